@@ -1,0 +1,157 @@
+/*
+ * sow_b200 -- C ABI of the B200-native SoW ("Sum-of-Weights", python package `tn_gradient`) training hot path.
+ *
+ * The reference (antoine311200/sow) is pure PyTorch and has no FFI of its own; its boundary for this path is the
+ * Python surface of `tn_gradient`.  This header is the boundary *underneath* that surface: every
+ * entry point names the reference call site (file:line under the reference root) whose device math it replaces.
+ *
+ * Conventions
+ *  - All pointers are BORROWED raw CUDA device pointers (except where marked host).  Nothing here allocates,
+ *    frees, synchronises the device, or keeps a pointer after returning.
+ *  - Every function returns 0 on success and a negative SOWB_E* code on failure; sow_last_error() returns a
+ *    thread-local human-readable message for the last failure on the calling thread.
+ *  - Work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); calls are re-entrant and may be
+ *    issued concurrently from several host threads (autograd runs backward on its own thread).
+ *  - Scratch memory is provided by the caller: ask sow_workspace_bytes() first.
+ *  - Matrices are dense row-major.  W is (in,out) -- the reference layout (tn_gradient/layer/sow.py:28,74-79),
+ *    i.e. the transpose of nn.Linear.  dtype codes: SOWB_BF16 / SOWB_F32.
+ *  - Alignment: device pointers 16-byte aligned; `in` and `out` multiples of 8 (TMA row pitch rule).
+ */
+#ifndef SOW_B200_H_
+#define SOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOWB_OK 0
+#define SOWB_EINVAL (-1)    /* bad argument (null pointer, unsupported shape/dtype, misalignment) */
+#define SOWB_EWORKSPACE (-2) /* workspace too small */
+#define SOWB_ECUDA (-3)     /* CUDA runtime / driver error (message has the CUDA error string) */
+#define SOWB_ENOTSUP (-4)   /* device is not sm_100 */
+
+#define SOWB_BF16 0
+#define SOWB_F32 1
+
+enum sowb_op {
+  SOWB_OP_LINEAR_FWD = 0,
+  SOWB_OP_LINEAR_BWD = 1,
+  SOWB_OP_MERGE = 2,
+  SOWB_OP_THIN_QR = 3,
+  SOWB_OP_TT_PROJECT = 4,
+};
+
+int sow_abi_version(void);
+const char* sow_last_error(void);
+
+/* Bytes of scratch the op needs for the given problem (T tokens, in/out features, rank r). */
+size_t sow_workspace_bytes(int op, int64_t T, int in, int out, int r);
+
+/* Rank padded to the k-block granularity used for the staged low-rank activations t / dt ([T, r_pad] bf16). */
+int sow_rank_pad(int r);
+
+/*
+ * SoW linear forward.   Replaces SoWLinear.forward, tn_gradient/layer/sow.py:107-126
+ *     y[T,out] = x[T,in] . W[in,out]  +  scale * (x . A[in,r]) . B[r,out]  (+ bias[out])
+ * W may be NULL (pre-merge phase: acc_downweight is empty, sow.py:69-70) -> rank-r term only.
+ * t_out[T, r_pad] (bf16) receives scale * x . A, the tensor autograd saves for backward.
+ */
+int sow_linear_fwd(const void* x, const void* W, const void* A, const void* B, const void* bias, void* y,
+                   void* t_out, int64_t T, int in, int out, int r, float scale, int dtype, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/*
+ * Factor gradients.   Replaces the MmBackward nodes autograd records at sow.py:117,119:
+ *     dt[T,r_pad] = scale * dY . B^T          dB[r,out] = t^T . dY          dA[in,r] = x^T . dt
+ * (t is the tensor saved by sow_linear_fwd, which already carries `scale`).  dbias[out] = sum_T dY if non-NULL.
+ * The full in x out weight gradient is never formed (W is frozen: sow.py:69-70, prepare.py:142,150).
+ */
+int sow_linear_bwd_factors(const void* dy, const void* x, const void* t, const void* B, void* dt, void* dA,
+                           void* dB, void* dbias, int64_t T, int in, int out, int r, float scale, int dtype,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Input gradient.   Replaces MmBackward of sow.py:112 and :117:
+ *     dX[T,in] = dY . W^T + dt . A^T          (W may be NULL -> second term only)
+ */
+int sow_linear_bwd_dx(const void* dy, const void* dt, const void* W, const void* A, void* dx, int64_t T, int in,
+                      int out, int r, int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * One entry of the grouped merge table (host memory, copied by the call).
+ * Replaces SoWLinear.accumulate's dense branch, sow.py:131-134,140,151-153:  W <- W_prev + scale * A . B
+ * W_prev may be NULL (first merge: W <- scale * A . B).  W and W_prev may alias (in-place RMW).
+ */
+typedef struct sowb_merge_entry {
+  void* W;            /* (in,out) destination                     */
+  const void* W_prev; /* (in,out) previous accumulation or NULL    */
+  const void* A;      /* (in,r)                                    */
+  const void* B;      /* (r,out)                                   */
+  int in, out, r;
+  float scale;
+} sowb_merge_entry;
+
+/* Grouped merge over n entries in ONE launch.  table_dev: device scratch of n * sow_merge_table_stride() bytes. */
+size_t sow_merge_table_stride(void);
+int sow_merge_grouped(const sowb_merge_entry* entries_host, int n, int dtype, void* table_dev,
+                      size_t table_bytes, void* stream);
+
+/*
+ * Thin QR of the first r columns:  Q[m,r] (orthonormal) spanning X[:, :r] where X is (m,n) row-major fp32 with
+ * leading dimension ldx.   Replaces the full-matrix torch.linalg.qr in qr_weight, tn_gradient/utils.py:19-22
+ * (only Q[:, :rank] is kept: sow.py:171) and the complete QR in TensorTrain.decompose, tn_gradient/tt.py:129-132.
+ * Batched: `batch` matrices, strides in elements.  Sign convention: R has non-negative diagonal.
+ */
+int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64_t q_batch_stride, int m, int r,
+                int batch, void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * TT projection  R[r,n] = Q[m,r]^T . L[m,n]  in fp32 (3xTF32-free, exact fp32 FMA accumulate).
+ * Replaces R[:right_rank,:] of the complete QR in tn_gradient/tt.py:129-133.  Batched like sow_thin_qr.
+ */
+int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q_batch_stride, float* R,
+               int64_t r_batch_stride, int m, int n, int r, int batch, void* stream);
+
+/*
+ * Fused pad + interleave for TensorTrain.from_matrix (tn_gradient/tt.py:48-67,33; utils.py:78-84), order 2:
+ *     out[(i1*nn+o1), (i2*nn+o2)] = src[i1*mm+i2, o1*nn+o2]   (zero where the source index is out of range)
+ * src is (M,N) row-major of dtype `dtype`; out is fp32 (mm*nn) x (mm*nn).
+ */
+int tt_interleave2(const void* src, int M, int N, int mm, int nn, float* out, int dtype, void* stream);
+
+/*
+ * Order-2 TT reconstruction fused with the TT-Adam update.  Replaces, per parameter,
+ * TensorTrain.reconstruct/to_matrix (tt.py:213-247) twice + the elementwise Adam of
+ * tn_gradient/optimizer/ttadam.py:71-111:
+ *     m = G1m . G2m ; v = max(G1v . G2v, 0)              (cores: G1 [(mm*nn), r], G2 [r, (mm*nn)], fp32)
+ *     m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
+ *     p -= step_size * m / (sqrt(v) + eps) ; p -= lr*wd*p  (if wd > 0)
+ * and writes the NEW m, v in the padded+interleaved layout of tt_interleave2 (fp32, (mm*nn)^2 each) ready for
+ * sow_thin_qr/tt_project, so the dense moments never round-trip HBM in (M,N) layout.
+ * first_step != 0 -> previous m, v are zero (cores ignored; ttadam.py:68-70,76-78).
+ */
+int tt_adam_fused2(void* p, const void* g, const float* G1m, const float* G2m, const float* G1v,
+                   const float* G2v, int r, float* m_out, float* v_out, int M, int N, int mm, int nn,
+                   float beta1, float beta2, float eps, float step_size, float lr_wd, int first_step, int dtype,
+                   void* stream);
+
+/*
+ * Generic dense Adam(W) over a flat list of tensors in one launch ("multi-tensor"), used for the factor group
+ * (torch.optim.AdamW at scripts/simple_train.py:502-506).  Pointers arrays are host arrays of device pointers.
+ * Moments have the parameter dtype (model.to(bf16): simple_train.py:425-426).  step_size/bias corrections are
+ * computed by the caller so that `state["step"]` semantics (reset_optimizer, training_utils.py:257-277) stay
+ * on the Python side.  decoupled != 0 -> AdamW (p *= 1 - lr*wd), else L2 (g += wd*p).
+ */
+int sow_adam_multi(void* const* p, const void* const* g, void* const* m, void* const* v, const int64_t* numel,
+                   int n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float bias_correction1, float bias_correction2, int decoupled, int dtype, void* table_dev,
+                   size_t table_bytes, void* stream);
+size_t sow_adam_table_bytes(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOW_B200_H_ */

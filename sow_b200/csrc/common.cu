@@ -1,0 +1,141 @@
+#include "common.cuh"
+
+#include <mutex>
+#include <string.h>
+#include <unordered_map>
+
+namespace sowb {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int num_sms() {
+  static std::mutex mu;
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+int require_sm100() {
+  static std::mutex mu;
+  static int cache[64] = {0};  // 0 unknown, 1 ok, -1 bad
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(SOWB_ECUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64) return SOWB_OK;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache[dev] == 0) {
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return set_error(SOWB_ECUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+    cache[dev] = (major == 10) ? 1 : -1;
+  }
+  if (cache[dev] < 0) return set_error(SOWB_ENOTSUP, "sow_b200 kernels require an sm_100 (B200) device");
+  return SOWB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor maps.  cuTensorMapEncodeTiled is resolved through the runtime so that the library has no link-time
+// dependency on libcuda (it must dlopen on the GPU-less build host).  Encoded maps are cached: weights and
+// workspaces keep their addresses across steps, so the steady state does no driver calls.
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* base;
+  uint64_t inner, outer, pitch;
+  uint32_t b0, b1;
+  int eb;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && pitch == o.pitch && b0 == o.b0 && b1 == o.b1 &&
+           eb == o.eb;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner * 0xC2B2AE3D27D4EB4Full) ^ (k.outer << 17) ^ (k.pitch << 29) ^ (uint64_t(k.b0) << 7) ^
+         (uint64_t(k.b1) << 43) ^ uint64_t(k.eb);
+    return static_cast<size_t>(h ^ (h >> 31));
+  }
+};
+
+int make_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                       uint32_t box_inner, uint32_t box_outer, int elem_bytes) {
+  if (base == nullptr) return set_error(SOWB_EINVAL, "tensor map: null base pointer");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return set_error(SOWB_EINVAL, "tensor map: base pointer %p is not 16-byte aligned", base);
+  if (pitch_bytes % 16 != 0)
+    return set_error(SOWB_EINVAL, "tensor map: row pitch %llu B is not a multiple of 16 (features must be multiples of 8)",
+                     (unsigned long long)pitch_bytes);
+  if (box_inner * elem_bytes != 128 || box_outer == 0 || box_outer > 256)
+    return set_error(SOWB_EINVAL, "tensor map: unsupported box %u x %u", box_inner, box_outer);
+
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{base, inner, outer, pitch_bytes, box_inner, box_outer, elem_bytes};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      memcpy(out, &it->second, sizeof(CUtensorMap));
+      return SOWB_OK;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(SOWB_ECUDA, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = (elem_bytes == 2) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(SOWB_ECUDA,
+                     "cuTensorMapEncodeTiled failed with CUresult %d (base %p inner %llu outer %llu pitch %llu box %ux%u)",
+                     (int)r, base, (unsigned long long)inner, (unsigned long long)outer,
+                     (unsigned long long)pitch_bytes, box_inner, box_outer);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 8192) cache.clear();  // activations churn addresses; weights re-enter immediately
+    cache.emplace(key, *out);
+  }
+  return SOWB_OK;
+}
+
+}  // namespace sowb
+
+extern "C" {
+int sow_abi_version(void) { return 1; }
+const char* sow_last_error(void) { return sowb::g_err; }
+}

@@ -1,0 +1,291 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] (+)= alpha * ( A[M,K] * B[K,N]  +  A2[M,K2] * B2[K2,N] )  (+ bias[N])
+//
+// One CTA per SM, 256 threads:
+//   warp 0 / lane 0 : TMA producer  (global -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1 / lane 0 : MMA issuer    (tcgen05.mma, M=128 x N=BN x K=16, fp32 accumulators in TMEM, 2 stages)
+//   warp 2          : TMEM allocator / deallocator
+//   warps 4..7      : epilogue      (tcgen05.ld -> registers -> {bf16 via swizzled smem + TMA store | fp32 red.add})
+//
+// Operand "majorness" is a template parameter because the SoW hot path needs all four combinations without
+// re-laying-out any user-visible tensor (reference layout of W is (in,out), tn_gradient/layer/sow.py:28,74-79):
+//   forward   y  = x.W      : A K-major,  B MN-major  (W rows are K, N contiguous)
+//   backward  dX = dY.W^T   : A K-major,  B K-major   (same W buffer, rows are N, K contiguous)
+//   backward  dA = x^T.dt   : A MN-major, B MN-major  (split-K over tokens, fp32 red.add epilogue)
+// The optional second operand pair (A2,B2) is the rank-r "tail": extra 64-deep k-blocks appended to the same
+// accumulator, which is how the low-rank term is fused into the base GEMM (no second pass over y / dX).
+#pragma once
+#include "ptx.cuh"
+
+namespace sowb {
+
+constexpr int kBM = 128;      // UMMA M (cta_group::1)
+constexpr int kBK = 64;       // k-block depth in elements (= one 128B swizzle span of bf16)
+constexpr int kUmmaK = 16;    // bf16 UMMA K
+constexpr int kGemmThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kStoreBoxCols = 64;                                  // bf16 columns per TMA store box (128 B)
+constexpr int kStageCBytes = kBM * kStoreBoxCols * 2;              // 16 KB per staging buffer
+
+enum EpiMode : int {
+  EPI_BF16_TMA = 0,    // D -> bf16, via smem staging + TMA store (clips M/N tails)
+  EPI_F32_ATOMIC = 1,  // D -> fp32 red.global.add into out_f32[row*ldc + col]  (split-K partial sums)
+};
+
+struct GemmParams {
+  int M, N;
+  int kb_main;         // number of kBK-deep k-blocks taken from (A ,B )
+  int kb_tail;         // number of kBK-deep k-blocks taken from (A2,B2)
+  int m_tiles, n_tiles, splits;
+  int kb_per_split;
+  float alpha;
+  const __nv_bfloat16* bias;  // nullable, length N (EPI_BF16_TMA only)
+  float* out_f32;             // EPI_F32_ATOMIC only
+  int ldc;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  // leave room for 2 staging buffers (32 KB) + barriers inside the 227 KB opt-in limit
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kStagingBytes = 2 * kStageCBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = 1024 /*align slack*/ + kRingBytes + kStagingBytes + kBarBytes;
+  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* staging = smem + S::kRingBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + S::kStagingBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + S::kStages;         // [kStages]
+  uint64_t* tfull_bar = bars + 2 * S::kStages;     // [2]
+  uint64_t* tempty_bar = bars + 2 * S::kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.kb_tail > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+    if (EPI == EPI_BF16_TMA) tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], kEpiThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, S::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_work = p.m_tiles * p.n_tiles * p.splits;
+  const int kb_total = p.kb_main + p.kb_tail;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w % p.splits;
+      const int tile = w / p.splits;
+      const int m0 = (tile / p.n_tiles) * kBM;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = ring + stage * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+        const bool tail = kb >= p.kb_main;
+        const CUtensorMap* ma = tail ? &tmA2 : &tmA;
+        const CUtensorMap* mb = tail ? &tmB2 : &tmB;
+        const int k0 = (tail ? kb - p.kb_main : kb) * kBK;
+        if (A_MN) {
+          // global [K rows, M contiguous]: two boxes of (64 M) x (64 K)
+#pragma unroll
+          for (int j = 0; j < kBM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &full_bar[stage], m0 + 64 * j, k0);
+        } else {
+          // global [M rows, K contiguous]: one box of (64 K) x (128 M)
+          tma_load_2d(sa, ma, &full_bar[stage], k0, m0);
+        }
+        if (B_MN) {
+          // global [K rows, N contiguous]: BN/64 boxes of (64 N) x (64 K)
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, mb, &full_bar[stage], n0 + 64 * j, k0);
+        } else {
+          // global [N rows, K contiguous]: one box of (64 K) x (BN N)
+          tma_load_2d(sb, mb, &full_bar[stage], k0, n0);
+        }
+        if (++stage == S::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // K-major:  SBO = 1024 B between 8-row atoms; advance 32 B per UMMA_K inside the 128 B swizzle span.
+    // MN-major: LBO = 8192 B between 64-wide MN blocks (one TMA box each), SBO = 1024 B between 8-deep K groups;
+    //           advance 2 K-groups = 2048 B per UMMA_K.
+    constexpr uint32_t a_lbo = A_MN ? 8192 : 16, a_sbo = 1024, a_kstep = A_MN ? 2048 : 32;
+    constexpr uint32_t b_lbo = B_MN ? 8192 : 16, b_sbo = 1024, b_kstep = B_MN ? 2048 : 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w % p.splits;
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + stage * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+          const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+          umma_bf16(tmem_d, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (++stage == S::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                  // TMEM lane quarter owned by this warp (warp % 4)
+    const int row_in_tile = q * 32 + lane;   // accumulator row == TMEM lane
+    const int et = threadIdx.x - 128;        // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t boxes_issued = 0;  // TMA-store boxes issued so far by this CTA (for staging double-buffer)
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tile = w / p.splits;
+      const int m0 = (tile / p.n_tiles) * kBM;
+      const int n0 = (tile % p.n_tiles) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (EPI == EPI_BF16_TMA) {
+#pragma unroll 1
+        for (int b = 0; b < BN / kStoreBoxCols; ++b) {
+          if (n0 + b * kStoreBoxCols >= p.N) break;  // uniform across the CTA
+          uint8_t* stg = staging + (boxes_issued & 1) * kStageCBytes;
+          if (boxes_issued >= 2) {
+            if (et == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+            named_barrier_sync(1, kEpiThreads);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(taddr + b * kStoreBoxCols + h * 32, v);
+            tmem_ld_wait();
+            const int colbase = n0 + b * kStoreBoxCols + h * 32;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[j] = p.alpha * __uint_as_float(v[c * 8 + j]);
+                if (p.bias != nullptr) {
+                  const int col = colbase + c * 8 + j;
+                  if (col < p.N) f[j] += __bfloat162float(p.bias[col]);
+                }
+              }
+              uint4 pk;
+              pk.x = pack_bf16x2(f[0], f[1]);
+              pk.y = pack_bf16x2(f[2], f[3]);
+              pk.z = pack_bf16x2(f[4], f[5]);
+              pk.w = pack_bf16x2(f[6], f[7]);
+              const int chunk = h * 4 + c;  // 16-byte chunk index inside the 128-byte row
+              *reinterpret_cast<uint4*>(stg + row_in_tile * 128 + ((chunk ^ (row_in_tile & 7)) << 4)) = pk;
+            }
+          }
+          fence_proxy_async_smem();
+          named_barrier_sync(1, kEpiThreads);
+          if (et == 0) {
+            tma_store_2d(&tmC, stg, n0 + b * kStoreBoxCols, m0);
+            tma_store_commit();
+          }
+          ++boxes_issued;
+        }
+      } else {
+        const int row = m0 + row_in_tile;
+#pragma unroll 1
+        for (int c32 = 0; c32 < BN / 32; ++c32) {
+          if (n0 + c32 * 32 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(taddr + c32 * 32, v);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float* dst = p.out_f32 + static_cast<size_t>(row) * p.ldc + n0 + c32 * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + c32 * 32 + j < p.N) atomicAdd(dst + j, p.alpha * __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (EPI == EPI_BF16_TMA && et == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, S::kTmemCols);
+}
+
+}  // namespace sowb

@@ -1,0 +1,292 @@
+// C-ABI entry points for the SoW linear forward / backward (include/sow_b200.h) on top of the tcgen05 GEMM.
+#include "common.cuh"
+#include "gemm.cuh"
+
+#include <algorithm>
+
+namespace sowb {
+
+// ------------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------------
+// A (in, r) -> A_pad (in, r_pad), zero padded: gives the factor a TMA-legal 128-byte row pitch.
+__global__ void pack_factor_kernel(const __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ A_pad, int in,
+                                   int r, int r_pad) {
+  const int64_t n = static_cast<int64_t>(in) * r_pad;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / r_pad), col = static_cast<int>(i % r_pad);
+    A_pad[i] = (col < r) ? A[static_cast<int64_t>(row) * r + col] : __float2bfloat16(0.f);
+  }
+}
+
+// fp32 split-K accumulators -> bf16 gradients in the reference layouts:
+//   dA[i, j] = accA[i, j]         (accA is [in , r_pad])
+//   dB[j, o] = accB[o, j]         (accB is [out, r_pad], i.e. dB^T)
+__global__ void finalize_factor_grads_kernel(const float* __restrict__ accA, const float* __restrict__ accB,
+                                             __nv_bfloat16* __restrict__ dA, __nv_bfloat16* __restrict__ dB, int in,
+                                             int out, int r, int r_pad) {
+  __shared__ float tile[32][33];
+  const int nA_blocks = ceil_div(in * r, 1024);
+  if (static_cast<int>(blockIdx.x) < nA_blocks) {
+    const int i = blockIdx.x * 1024 + threadIdx.y * 32 + threadIdx.x;
+    if (i < in * r) {
+      const int row = i / r, col = i % r;
+      dA[i] = __float2bfloat16(accA[static_cast<int64_t>(row) * r_pad + col]);
+    }
+    return;
+  }
+  // transpose tiles of accB: block handles 32 (o) x 32 (j)
+  const int b = blockIdx.x - nA_blocks;
+  const int jt = ceil_div(r, 32);
+  const int o0 = (b / jt) * 32, j0 = (b % jt) * 32;
+  {
+    const int o = o0 + threadIdx.y, j = j0 + threadIdx.x;
+    tile[threadIdx.y][threadIdx.x] = (o < out && j < r) ? accB[static_cast<int64_t>(o) * r_pad + j] : 0.f;
+  }
+  __syncthreads();
+  {
+    const int j = j0 + threadIdx.y, o = o0 + threadIdx.x;
+    if (o < out && j < r) dB[static_cast<int64_t>(j) * out + o] = __float2bfloat16(tile[threadIdx.x][threadIdx.y]);
+  }
+}
+
+// dbias[o] = sum_t dY[t, o]: block = 64 columns x 4 row-lanes, grid.y splits T; fp32 atomics then convert.
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ acc, int64_t T, int out) {
+  const int col = blockIdx.x * 64 + threadIdx.x;
+  if (col >= out) return;
+  const int64_t rows_per = (T + gridDim.y - 1) / gridDim.y;
+  const int64_t t0 = blockIdx.y * rows_per, t1 = min(T, t0 + rows_per);
+  float s = 0.f;
+  for (int64_t t = t0 + threadIdx.y; t < t1; t += blockDim.y) s += __bfloat162float(dy[t * out + col]);
+  atomicAdd(acc + col, s);
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launcher
+// ------------------------------------------------------------------------------------------------
+struct Operand {
+  const void* ptr;
+  uint64_t rows, cols;  // as stored in global memory, row-major, `cols` contiguous
+  uint64_t pitch_elems;
+};
+
+// Operand A of D = A.B: logical [M, K].  K-major  <=> stored [M rows, K cols];  MN-major <=> stored [K rows, M cols].
+// Operand B of D = A.B: logical [K, N].  K-major  <=> stored [N rows, K cols];  MN-major <=> stored [K rows, N cols].
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const Operand& A, const Operand& B, const Operand* A2, const Operand* B2, void* C_bf16,
+                       float* C_f32, int ldc, int M, int N, int K, int K2, float alpha, const void* bias,
+                       bool split_k, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmC;
+  int rc;
+  rc = make_tensor_map_2d(&tmA, A.ptr, A.cols, A.rows, A.pitch_elems * 2, 64, A_MN ? 64 : kBM, 2);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tmB, B.ptr, B.cols, B.rows, B.pitch_elems * 2, 64, B_MN ? 64 : BN, 2);
+  if (rc) return rc;
+  tmA2 = tmA;
+  tmB2 = tmB;
+  if (K2 > 0) {
+    rc = make_tensor_map_2d(&tmA2, A2->ptr, A2->cols, A2->rows, A2->pitch_elems * 2, 64, A_MN ? 64 : kBM, 2);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tmB2, B2->ptr, B2->cols, B2->rows, B2->pitch_elems * 2, 64, B_MN ? 64 : BN, 2);
+    if (rc) return rc;
+  }
+  tmC = tmA;
+  if (EPI == EPI_BF16_TMA) {
+    rc = make_tensor_map_2d(&tmC, C_bf16, N, M, static_cast<uint64_t>(ldc) * 2, kStoreBoxCols, kBM, 2);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.kb_main = ceil_div(K, kBK);
+  p.kb_tail = ceil_div(K2, kBK);
+  p.m_tiles = ceil_div(M, kBM);
+  p.n_tiles = ceil_div(N, BN);
+  const int kb_total = p.kb_main + p.kb_tail;
+  const int sms = num_sms();
+  int splits = 1;
+  if (split_k) {
+    splits = sms / (p.m_tiles * p.n_tiles);
+    if (splits < 1) splits = 1;
+    if (splits > kb_total) splits = kb_total;
+  }
+  p.kb_per_split = ceil_div(kb_total, splits);
+  p.splits = ceil_div(kb_total, p.kb_per_split);
+  p.alpha = alpha;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.out_f32 = C_f32;
+  p.ldc = ldc;
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  if (total <= 0 || kb_total <= 0) return SOWB_OK;
+  auto kern = sow_gemm_kernel<BN, A_MN, B_MN, EPI>;
+  SOWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  const int grid = total < sms ? total : sms;
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmA2, tmB2, tmC, p);
+  SOWB_CHECK_CUDA(cudaGetLastError());
+  return SOWB_OK;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static int check_common(const char* fn, int64_t T, int in, int out, int r, int dtype) {
+  if (dtype != SOWB_BF16)
+    return set_error(SOWB_EINVAL, "%s: only SOWB_BF16 is implemented on device (fp32 modules use the host-side bf16 compute policy)", fn);
+  if (T <= 0 || in <= 0 || out <= 0 || r <= 0) return set_error(SOWB_EINVAL, "%s: non-positive dimension", fn);
+  if (in % 8 != 0 || out % 8 != 0)
+    return set_error(SOWB_EINVAL, "%s: in=%d and out=%d must be multiples of 8 (16-byte TMA row pitch)", fn, in, out);
+  if (T >= (int64_t(1) << 31)) return set_error(SOWB_EINVAL, "%s: T too large", fn);
+  return require_sm100();
+}
+
+}  // namespace sowb
+
+using namespace sowb;
+
+extern "C" {
+
+int sow_rank_pad(int r) { return round_up(r, kBK); }
+
+size_t sow_workspace_bytes(int op, int64_t T, int in, int out, int r) {
+  const size_t r_pad = round_up(r, kBK);
+  switch (op) {
+    case SOWB_OP_LINEAR_FWD:
+      return align256(size_t(in) * r_pad * 2);
+    case SOWB_OP_LINEAR_BWD:
+      // max(bwd_factors, bwd_dx): fp32 accumulators for dA, dB^T, dbias | padded A
+      return align256(size_t(in) * r_pad * 4) + align256(size_t(out) * r_pad * 4) + align256(size_t(out) * 4) +
+             align256(size_t(in) * r_pad * 2);
+    default:
+      return 0;
+  }
+}
+
+int sow_linear_fwd(const void* x, const void* W, const void* A, const void* B, const void* bias, void* y,
+                   void* t_out, int64_t T, int in, int out, int r, float scale, int dtype, void* ws,
+                   size_t ws_bytes, void* stream_) {
+  int rc = check_common("sow_linear_fwd", T, in, out, r, dtype);
+  if (rc) return rc;
+  SOWB_REQUIRE(x && A && B && y && t_out && ws, "sow_linear_fwd: null pointer argument");
+  if (ws_bytes < sow_workspace_bytes(SOWB_OP_LINEAR_FWD, T, in, out, r))
+    return set_error(SOWB_EWORKSPACE, "sow_linear_fwd: workspace %zu B < required %zu B", ws_bytes,
+                     sow_workspace_bytes(SOWB_OP_LINEAR_FWD, T, in, out, r));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int r_pad = round_up(r, kBK);
+  __nv_bfloat16* A_pad = static_cast<__nv_bfloat16*>(ws);
+
+  {
+    const int64_t n = int64_t(in) * r_pad;
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096));
+    pack_factor_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), A_pad, in, r, r_pad);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+  }
+  // t = scale * x . A_pad            [T, r_pad]
+  Operand opX{x, uint64_t(T), uint64_t(in), uint64_t(in)};
+  Operand opApadMN{A_pad, uint64_t(in), uint64_t(r_pad), uint64_t(r_pad)};  // [K=in rows, N=r_pad cols]
+  rc = launch_gemm<64, false, true, EPI_BF16_TMA>(opX, opApadMN, nullptr, nullptr, t_out, nullptr, r_pad,
+                                                  static_cast<int>(T), r_pad, in, 0, scale, nullptr, false, stream);
+  if (rc) return rc;
+  // y = x . W + t . B (+ bias)
+  Operand opT{t_out, uint64_t(T), uint64_t(r_pad), uint64_t(r_pad)};
+  Operand opBMN{B, uint64_t(r), uint64_t(out), uint64_t(out)};  // [K=r rows (OOB rows read as 0), N=out cols]
+  if (W != nullptr) {
+    Operand opWMN{W, uint64_t(in), uint64_t(out), uint64_t(out)};  // [K=in rows, N=out cols]
+    rc = launch_gemm<256, false, true, EPI_BF16_TMA>(opX, opWMN, &opT, &opBMN, y, nullptr, out, static_cast<int>(T),
+                                                     out, in, r_pad, 1.0f, bias, false, stream);
+  } else {
+    rc = launch_gemm<256, false, true, EPI_BF16_TMA>(opT, opBMN, nullptr, nullptr, y, nullptr, out,
+                                                     static_cast<int>(T), out, r_pad, 0, 1.0f, bias, false, stream);
+  }
+  return rc;
+}
+
+int sow_linear_bwd_factors(const void* dy, const void* x, const void* t, const void* B, void* dt, void* dA,
+                           void* dB, void* dbias, int64_t T, int in, int out, int r, float scale, int dtype,
+                           void* ws, size_t ws_bytes, void* stream_) {
+  int rc = check_common("sow_linear_bwd_factors", T, in, out, r, dtype);
+  if (rc) return rc;
+  SOWB_REQUIRE(dy && x && t && B && dt && dA && dB && ws, "sow_linear_bwd_factors: null pointer argument");
+  if (ws_bytes < sow_workspace_bytes(SOWB_OP_LINEAR_BWD, T, in, out, r))
+    return set_error(SOWB_EWORKSPACE, "sow_linear_bwd_factors: workspace %zu B < required %zu B", ws_bytes,
+                     sow_workspace_bytes(SOWB_OP_LINEAR_BWD, T, in, out, r));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int r_pad = round_up(r, kBK);
+  uint8_t* wsp = static_cast<uint8_t*>(ws);
+  float* accA = reinterpret_cast<float*>(wsp);
+  float* accB = reinterpret_cast<float*>(wsp + align256(size_t(in) * r_pad * 4));
+  float* accBias = reinterpret_cast<float*>(wsp + align256(size_t(in) * r_pad * 4) + align256(size_t(out) * r_pad * 4));
+  const size_t acc_bytes = align256(size_t(in) * r_pad * 4) + align256(size_t(out) * r_pad * 4) + align256(size_t(out) * 4);
+  SOWB_CHECK_CUDA(cudaMemsetAsync(wsp, 0, acc_bytes, stream));
+
+  // dt = scale * dY . B^T     [T, r_pad]; B is read K-major: [N=r rows (OOB rows -> 0), K=out cols]
+  Operand opDY{dy, uint64_t(T), uint64_t(out), uint64_t(out)};
+  Operand opBK{B, uint64_t(r), uint64_t(out), uint64_t(out)};
+  rc = launch_gemm<64, false, false, EPI_BF16_TMA>(opDY, opBK, nullptr, nullptr, dt, nullptr, r_pad,
+                                                   static_cast<int>(T), r_pad, out, 0, scale, nullptr, false, stream);
+  if (rc) return rc;
+  // dB^T [out, r_pad] = dY^T . t   (both operands MN-major; K = T, split-K with fp32 red.add)
+  Operand opT{t, uint64_t(T), uint64_t(r_pad), uint64_t(r_pad)};
+  rc = launch_gemm<64, true, true, EPI_F32_ATOMIC>(opDY, opT, nullptr, nullptr, nullptr, accB, r_pad, out, r_pad,
+                                                   static_cast<int>(T), 0, 1.0f, nullptr, true, stream);
+  if (rc) return rc;
+  // dA [in, r_pad] = x^T . dt
+  Operand opX{x, uint64_t(T), uint64_t(in), uint64_t(in)};
+  Operand opDT{dt, uint64_t(T), uint64_t(r_pad), uint64_t(r_pad)};
+  rc = launch_gemm<64, true, true, EPI_F32_ATOMIC>(opX, opDT, nullptr, nullptr, nullptr, accA, r_pad, in, r_pad,
+                                                   static_cast<int>(T), 0, 1.0f, nullptr, true, stream);
+  if (rc) return rc;
+  {
+    const int nA_blocks = ceil_div(in * r, 1024);
+    const int nB_blocks = ceil_div(out, 32) * ceil_div(r, 32);
+    finalize_factor_grads_kernel<<<nA_blocks + nB_blocks, dim3(32, 32), 0, stream>>>(
+        accA, accB, static_cast<__nv_bfloat16*>(dA), static_cast<__nv_bfloat16*>(dB), in, out, r, r_pad);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (dbias != nullptr) {
+    dim3 grid(ceil_div(out, 64), static_cast<unsigned>(std::min<int64_t>(64, (T + 255) / 256)));
+    colsum_kernel<<<grid, dim3(64, 4), 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), accBias, T, out);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    f32_to_bf16_kernel<<<ceil_div(out, 256), 256, 0, stream>>>(accBias, static_cast<__nv_bfloat16*>(dbias), out);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+  }
+  return SOWB_OK;
+}
+
+int sow_linear_bwd_dx(const void* dy, const void* dt, const void* W, const void* A, void* dx, int64_t T, int in,
+                      int out, int r, int dtype, void* ws, size_t ws_bytes, void* stream_) {
+  int rc = check_common("sow_linear_bwd_dx", T, in, out, r, dtype);
+  if (rc) return rc;
+  SOWB_REQUIRE(dy && dt && A && dx && ws, "sow_linear_bwd_dx: null pointer argument");
+  const int r_pad = round_up(r, kBK);
+  if (ws_bytes < align256(size_t(in) * r_pad * 2))
+    return set_error(SOWB_EWORKSPACE, "sow_linear_bwd_dx: workspace %zu B < required %zu B", ws_bytes,
+                     align256(size_t(in) * r_pad * 2));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  __nv_bfloat16* A_pad = static_cast<__nv_bfloat16*>(ws);
+  {
+    const int64_t n = int64_t(in) * r_pad;
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096));
+    pack_factor_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), A_pad, in, r, r_pad);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+  }
+  // dX = dY . W^T + dt . A_pad^T ;  W (in,out) is K-major for this product: [N=in rows, K=out cols]
+  Operand opDT{dt, uint64_t(T), uint64_t(r_pad), uint64_t(r_pad)};
+  Operand opApadK{A_pad, uint64_t(in), uint64_t(r_pad), uint64_t(r_pad)};  // [N=in rows, K=r_pad cols]
+  if (W != nullptr) {
+    Operand opDY{dy, uint64_t(T), uint64_t(out), uint64_t(out)};
+    Operand opWK{W, uint64_t(in), uint64_t(out), uint64_t(out)};
+    rc = launch_gemm<256, false, false, EPI_BF16_TMA>(opDY, opWK, &opDT, &opApadK, dx, nullptr, in,
+                                                      static_cast<int>(T), in, out, r_pad, 1.0f, nullptr, false, stream);
+  } else {
+    rc = launch_gemm<256, false, false, EPI_BF16_TMA>(opDT, opApadK, nullptr, nullptr, dx, nullptr, in,
+                                                      static_cast<int>(T), in, r_pad, 0, 1.0f, nullptr, false, stream);
+  }
+  return rc;
+}
+
+}  // extern "C"
