@@ -106,7 +106,7 @@ int sow_merge_grouped(const sowb_merge_entry* entries_host, int n, int dtype, vo
  * Batched: `batch` matrices, strides in elements.  Sign convention: R has non-negative diagonal.
  */
 int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64_t q_batch_stride, int m, int r,
-                int batch, void* ws, size_t ws_bytes, void* stream);
+                int batch, void* ws /* >= batch*m*r*4 bytes */, size_t ws_bytes, void* stream);
 
 /*
  * TT projection  R[r,n] = Q[m,r]^T . L[m,n]  in fp32 (3xTF32-free, exact fp32 FMA accumulate).
@@ -116,11 +116,16 @@ int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q
                int64_t r_batch_stride, int m, int n, int r, int batch, void* stream);
 
 /*
- * Fused pad + interleave for TensorTrain.from_matrix (tn_gradient/tt.py:48-67,33; utils.py:78-84), order 2:
- *     out[(i1*nn+o1), (i2*nn+o2)] = src[i1*mm+i2, o1*nn+o2]   (zero where the source index is out of range)
- * src is (M,N) row-major of dtype `dtype`; out is fp32 (mm*nn) x (mm*nn).
+ * Fused pad + interleave for TensorTrain.from_matrix / from_tensor (tn_gradient/tt.py:48-67,33; utils.py:78-84),
+ * any order d <= 8:   out[i1,o1,i2,o2,...,id,od] = src[(i1..id)_mm , (o1..od)_nn]   (0 outside (M,N))
+ * src is (M,N) row-major of dtype `dtype`; out is fp32 with (mm*nn)^d elements.  tt_deinterleave is the inverse
+ * restricted to (M,N) (TensorTrain.to_matrix, tt.py:242-247 + unpad_matrix, utils.py:86-87).
  */
-int tt_interleave2(const void* src, int M, int N, int mm, int nn, float* out, int dtype, void* stream);
+int tt_interleave(const void* src, int M, int N, int mm, int nn, int order, float* out, int dtype, void* stream);
+int tt_deinterleave(const float* src, int M, int N, int mm, int nn, int order, void* out, int dtype, void* stream);
+
+/* fp32 C[m,n] = A[m,r] . B[r,n] with small r: one link of the reconstruction chain (tt.py:213-237). */
+int tt_matmul_rk(const float* A, const float* B, float* C, int m, int n, int r, void* stream);
 
 /*
  * Order-2 TT reconstruction fused with the TT-Adam update.  Replaces, per parameter,
@@ -129,27 +134,32 @@ int tt_interleave2(const void* src, int M, int N, int mm, int nn, float* out, in
  *     m = G1m . G2m ; v = max(G1v . G2v, 0)              (cores: G1 [(mm*nn), r], G2 [r, (mm*nn)], fp32)
  *     m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
  *     p -= step_size * m / (sqrt(v) + eps) ; p -= lr*wd*p  (if wd > 0)
- * and writes the NEW m, v in the padded+interleaved layout of tt_interleave2 (fp32, (mm*nn)^2 each) ready for
+ * and writes the NEW m, v in the padded+interleaved layout of tt_interleave (fp32, (mm*nn)^2 each) ready for
  * sow_thin_qr/tt_project, so the dense moments never round-trip HBM in (M,N) layout.
  * first_step != 0 -> previous m, v are zero (cores ignored; ttadam.py:68-70,76-78).
  */
 int tt_adam_fused2(void* p, const void* g, const float* G1m, const float* G2m, const float* G1v,
                    const float* G2v, int r, float* m_out, float* v_out, int M, int N, int mm, int nn,
-                   float beta1, float beta2, float eps, float step_size, float lr_wd, int first_step, int dtype,
-                   void* stream);
+                   double beta1, double beta2, double eps, double step_size, double lr_wd, int first_step,
+                   int dtype, void* stream);
+
+/* Same update on dense fp32 moments m, v of shape (M,N) (order > 2 path); v is clamped at 0 first (ttadam.py:84). */
+int tt_adam_dense(void* p, const void* g, float* m, float* v, int64_t numel, double beta1, double beta2, double eps,
+                  double step_size, double lr_wd, int dtype, void* stream);
 
 /*
- * Generic dense Adam(W) over a flat list of tensors in one launch ("multi-tensor"), used for the factor group
- * (torch.optim.AdamW at scripts/simple_train.py:502-506).  Pointers arrays are host arrays of device pointers.
- * Moments have the parameter dtype (model.to(bf16): simple_train.py:425-426).  step_size/bias corrections are
- * computed by the caller so that `state["step"]` semantics (reset_optimizer, training_utils.py:257-277) stay
- * on the Python side.  decoupled != 0 -> AdamW (p *= 1 - lr*wd), else L2 (g += wd*p).
+ * Multi-tensor Adam / AdamW: one launch over a device table of chunks
+ *     struct { void* p; const void* g; void* m; void* v; int64_t n; }   (40 bytes, n <= sow_adam_chunk_elems())
+ * covering all tensors of a param group (torch.optim.AdamW at scripts/simple_train.py:502-506).  Moments have
+ * the parameter dtype (model.to(bf16): simple_train.py:425-426); math is fp32 in registers.  Bias corrections
+ * are computed by the caller so `state["step"]` semantics (reset_optimizer, training_utils.py:257-277) stay on
+ * the host side.  Hyper-parameters are doubles so that 1-beta is formed without float cancellation.
+ * decoupled != 0 -> AdamW (p *= 1 - lr*wd), else L2 (g += wd*p).
  */
-int sow_adam_multi(void* const* p, const void* const* g, void* const* m, void* const* v, const int64_t* numel,
-                   int n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float bias_correction1, float bias_correction2, int decoupled, int dtype, void* table_dev,
-                   size_t table_bytes, void* stream);
-size_t sow_adam_table_bytes(int n);
+int sow_adam_chunk_elems(void);
+int sow_adam_multi(const void* chunks_dev, int n_chunks, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, double bias_correction1, double bias_correction2, int decoupled, int dtype,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,7 @@ class MergeEntry(ctypes.Structure):
 
 
 _vp, _i, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+_d = ctypes.c_double
 
 # name -> (restype, argtypes).  Must list every symbol include/sow_b200.h declares (tests/test_abi.py checks).
 SIGNATURES = {
@@ -54,10 +55,13 @@ SIGNATURES = {
     "sow_merge_grouped": (_i, [ctypes.POINTER(MergeEntry), _i, _i, _vp, _sz, _vp]),
     "sow_thin_qr": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp, _sz, _vp]),
     "tt_project": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
-    "tt_interleave2": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
-    "tt_adam_fused2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _i, _vp]),
-    "sow_adam_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _vp, _sz, _vp]),
-    "sow_adam_table_bytes": (_sz, [_i]),
+    "tt_interleave": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "tt_deinterleave": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "tt_matmul_rk": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "tt_adam_fused2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i, _vp]),
+    "tt_adam_dense": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _vp]),
+    "sow_adam_chunk_elems": (_i, []),
+    "sow_adam_multi": (_i, [_vp, _i, _d, _d, _d, _d, _d, _d, _d, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,308 @@
+"""torch-level wrappers over the C ABI (include/sow_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams.  All device math happens inside libsow_b200.so.
+Every wrapper requires CUDA tensors and raises otherwise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SOWB_BF16, SOWB_F32, MergeEntry, SowB200Error, check
+
+# count of kernel-launching C-ABI calls, for bench.py's `gpu_launches` accounting (approximate kernels per call
+# are listed next to each call site)
+launch_counter = {"kernels": 0}
+
+_ws_lock = threading.Lock()
+_workspaces = {}
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise SowB200Error(
+                "sow_b200 ops need CUDA tensors: the SoW hot path is implemented as sm_100a kernels only "
+                "(no CPU fallback).  Move the module / tensors to a B200 device."
+            )
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.bfloat16:
+        return SOWB_BF16
+    if dt == torch.float32:
+        return SOWB_F32
+    raise SowB200Error(f"unsupported dtype {dt}")
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand.  Kernels that share a stream are serialised, so one
+    buffer per stream is enough; a bigger request replaces the buffer (the old one stays alive until the work
+    queued on it finishes because the caching allocator is stream-ordered)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    with _ws_lock:
+        buf = _workspaces.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            _workspaces[key] = buf
+    return buf
+
+
+def rank_pad(r: int) -> int:
+    return (r + 63) // 64 * 64
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SoW linear
+# ---------------------------------------------------------------------------------------------------------
+
+def linear_fwd(x: torch.Tensor, W: Optional[torch.Tensor], A: torch.Tensor, B: torch.Tensor,
+               bias: Optional[torch.Tensor], scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """y = x.W + scale*(x.A).B (+bias);  x (T,in) bf16 contiguous.  Returns (y (T,out), t (T,r_pad))."""
+    _require_cuda(x, W, A, B, bias)
+    lib = _lib.load()
+    T, fin = x.shape
+    r, fout = B.shape
+    rp = rank_pad(r)
+    y = torch.empty((T, fout), dtype=torch.bfloat16, device=x.device)
+    t = torch.empty((T, rp), dtype=torch.bfloat16, device=x.device)
+    nws = lib.sow_workspace_bytes(_lib.OP_LINEAR_FWD, T, fin, fout, r)
+    ws = workspace(x.device, nws)
+    rc = lib.sow_linear_fwd(_p(x), _p(W), _p(A), _p(B), _p(bias), _p(y), _p(t), T, fin, fout, r, float(scale),
+                            SOWB_BF16, _p(ws), ws.numel(), _stream_ptr(x.device))
+    check(rc, "sow_linear_fwd")
+    launch_counter["kernels"] += 3
+    return y, t
+
+
+def linear_bwd_factors(dy, x, t, B, scale: float, want_dbias: bool, fin: int):
+    """Returns (dt (T,r_pad), dA (in,r), dB (r,out), dbias or None)."""
+    _require_cuda(dy, x, t, B)
+    lib = _lib.load()
+    T, fout = dy.shape
+    r = B.shape[0]
+    rp = rank_pad(r)
+    dev = dy.device
+    dt = torch.empty((T, rp), dtype=torch.bfloat16, device=dev)
+    dA = torch.empty((fin, r), dtype=torch.bfloat16, device=dev)
+    dB = torch.empty((r, fout), dtype=torch.bfloat16, device=dev)
+    dbias = torch.empty((fout,), dtype=torch.bfloat16, device=dev) if want_dbias else None
+    nws = lib.sow_workspace_bytes(_lib.OP_LINEAR_BWD, T, fin, fout, r)
+    ws = workspace(dev, nws)
+    rc = lib.sow_linear_bwd_factors(_p(dy), _p(x), _p(t), _p(B), _p(dt), _p(dA), _p(dB), _p(dbias), T, fin, fout, r,
+                                    float(scale), SOWB_BF16, _p(ws), ws.numel(), _stream_ptr(dev))
+    check(rc, "sow_linear_bwd_factors")
+    launch_counter["kernels"] += 5 + (2 if want_dbias else 0)
+    return dt, dA, dB, dbias
+
+
+def linear_bwd_dx(dy, dt, W, A):
+    _require_cuda(dy, dt, W, A)
+    lib = _lib.load()
+    T, fout = dy.shape
+    fin, r = A.shape
+    dx = torch.empty((T, fin), dtype=torch.bfloat16, device=dy.device)
+    nws = lib.sow_workspace_bytes(_lib.OP_LINEAR_BWD, T, fin, fout, r)
+    ws = workspace(dy.device, nws)
+    rc = lib.sow_linear_bwd_dx(_p(dy), _p(dt), _p(W), _p(A), _p(dx), T, fin, fout, r, SOWB_BF16, _p(ws), ws.numel(),
+                               _stream_ptr(dy.device))
+    check(rc, "sow_linear_bwd_dx")
+    launch_counter["kernels"] += 2
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------------------
+# grouped merge
+# ---------------------------------------------------------------------------------------------------------
+
+def merge_grouped(items: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor, torch.Tensor, float]]):
+    """items: (W_out (in,out), W_prev or None, A (in,r), B (r,out), scale), all bf16 CUDA contiguous on one
+    device.  One launch per 64-wide rank chunk for the whole list."""
+    if not items:
+        return
+    lib = _lib.load()
+    dev = items[0][0].device
+    n = len(items)
+    arr = (MergeEntry * n)()
+    for i, (W, Wp, A, B, s) in enumerate(items):
+        _require_cuda(W, Wp, A, B)
+        for tname, tt in (("W", W), ("W_prev", Wp), ("A", A), ("B", B)):
+            if tt is not None and (tt.dtype != torch.bfloat16 or not tt.is_contiguous()):
+                raise SowB200Error(f"merge_grouped: {tname} must be a contiguous bf16 tensor")
+        fin, r = A.shape
+        fout = B.shape[1]
+        if tuple(W.shape) != (fin, fout) or B.shape[0] != r:
+            raise SowB200Error("merge_grouped: shape mismatch")
+        arr[i].W = W.data_ptr()
+        arr[i].W_prev = Wp.data_ptr() if Wp is not None else None
+        arr[i].A = A.data_ptr()
+        arr[i].B = B.data_ptr()
+        arr[i].in_features, arr[i].out_features, arr[i].r = fin, fout, r
+        arr[i].scale = float(s)
+    stride = lib.sow_merge_table_stride()
+    table = workspace(dev, n * stride + 256)
+    base = table.data_ptr()
+    aligned = (base + 127) // 128 * 128
+    rc = lib.sow_merge_grouped(arr, n, SOWB_BF16, ctypes.c_void_p(aligned), table.numel() - (aligned - base),
+                               _stream_ptr(dev))
+    check(rc, "sow_merge_grouped")
+    launch_counter["kernels"] += max((a[2].shape[1] + 63) // 64 for a in items)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# thin QR / TT pieces
+# ---------------------------------------------------------------------------------------------------------
+
+def thin_qr(X: torch.Tensor, r: int) -> torch.Tensor:
+    """Orthonormal basis Q (.., m, r) of the first r columns of X (.., m, n) fp32; batched over leading dims."""
+    _require_cuda(X)
+    if X.dtype != torch.float32:
+        raise SowB200Error("thin_qr expects fp32 input")
+    lib = _lib.load()
+    squeeze = X.dim() == 2
+    Xb = X.unsqueeze(0) if squeeze else X
+    if Xb.dim() != 3 or Xb.stride(2) != 1 or Xb.stride(1) < Xb.shape[2]:
+        Xb = Xb.contiguous()
+    b, m, n = Xb.shape
+    Q = torch.empty((b, m, r), dtype=torch.float32, device=X.device)
+    work = torch.empty((b, r, m), dtype=torch.float32, device=X.device)  # column-major CGS2 work copy
+    rc = lib.sow_thin_qr(_p(Xb), Xb.stride(0), Xb.stride(1), _p(Q), m * r, m, r, b, _p(work), work.numel() * 4,
+                         _stream_ptr(X.device))
+    check(rc, "sow_thin_qr")
+    launch_counter["kernels"] += 1
+    return Q[0] if squeeze else Q
+
+
+def project(L: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
+    """R (.., r, n) = Q^T (.., m, r) . L (.., m, n), fp32."""
+    _require_cuda(L, Q)
+    lib = _lib.load()
+    squeeze = L.dim() == 2
+    Lb = (L.unsqueeze(0) if squeeze else L).contiguous()
+    Qb = (Q.unsqueeze(0) if squeeze else Q).contiguous()
+    b, m, n = Lb.shape
+    r = Qb.shape[2]
+    R = torch.empty((b, r, n), dtype=torch.float32, device=L.device)
+    rc = lib.tt_project(_p(Lb), m * n, _p(Qb), m * r, _p(R), r * n, m, n, r, b, _stream_ptr(L.device))
+    check(rc, "tt_project")
+    launch_counter["kernels"] += 2
+    return R[0] if squeeze else R
+
+
+def interleave(src: torch.Tensor, mm: int, nn: int, order: int) -> torch.Tensor:
+    """(M,N) bf16/fp32 -> zero-padded, (i1,o1,...,id,od)-ordered fp32 flat tensor of (mm*nn)^order elements."""
+    _require_cuda(src)
+    lib = _lib.load()
+    src = src.contiguous()
+    M, N = src.shape
+    out = torch.empty(((mm * nn) ** order,), dtype=torch.float32, device=src.device)
+    rc = lib.tt_interleave(_p(src), M, N, mm, nn, order, _p(out), _dtype_code(src.dtype), _stream_ptr(src.device))
+    check(rc, "tt_interleave")
+    launch_counter["kernels"] += 1
+    return out
+
+
+def deinterleave(src: torch.Tensor, M: int, N: int, mm: int, nn: int, order: int, dtype=torch.float32) -> torch.Tensor:
+    _require_cuda(src)
+    lib = _lib.load()
+    src = src.contiguous()
+    out = torch.empty((M, N), dtype=dtype, device=src.device)
+    rc = lib.tt_deinterleave(_p(src), M, N, mm, nn, order, _p(out), _dtype_code(dtype), _stream_ptr(src.device))
+    check(rc, "tt_deinterleave")
+    launch_counter["kernels"] += 1
+    return out
+
+
+def matmul_rk(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """fp32 C = A (m,r) . B (r,n) for small r."""
+    _require_cuda(A, B)
+    lib = _lib.load()
+    A = A.contiguous()
+    B = B.contiguous()
+    m, r = A.shape
+    n = B.shape[1]
+    C = torch.empty((m, n), dtype=torch.float32, device=A.device)
+    rc = lib.tt_matmul_rk(_p(A), _p(B), _p(C), m, n, r, _stream_ptr(A.device))
+    check(rc, "tt_matmul_rk")
+    launch_counter["kernels"] += 1
+    return C
+
+
+def tt_adam_fused2(p, g, cores_m, cores_v, mm, nn, beta1, beta2, eps, step_size, lr_wd, first_step):
+    """Order-2 fused reconstruct + Adam.  Returns (m_new, v_new) as (P,P) fp32 interleaved matrices, P = mm*nn."""
+    _require_cuda(p, g)
+    lib = _lib.load()
+    M, N = p.shape
+    P = mm * nn
+    m_out = torch.empty((P, P), dtype=torch.float32, device=p.device)
+    v_out = torch.empty((P, P), dtype=torch.float32, device=p.device)
+    if first_step:
+        G1m = G2m = G1v = G2v = None
+        r = 1
+    else:
+        G1m, G2m = cores_m
+        G1v, G2v = cores_v
+        r = G1m.shape[-1]
+    g = g.contiguous()
+    rc = lib.tt_adam_fused2(_p(p), _p(g), _p(G1m), _p(G2m), _p(G1v), _p(G2v), r, _p(m_out), _p(v_out), M, N, mm, nn,
+                            float(beta1), float(beta2), float(eps), float(step_size), float(lr_wd),
+                            1 if first_step else 0, _dtype_code(p.dtype), _stream_ptr(p.device))
+    check(rc, "tt_adam_fused2")
+    launch_counter["kernels"] += 1
+    return m_out, v_out
+
+
+def tt_adam_dense(p, g, m, v, beta1, beta2, eps, step_size, lr_wd):
+    _require_cuda(p, g, m, v)
+    lib = _lib.load()
+    g = g.contiguous()
+    rc = lib.tt_adam_dense(_p(p), _p(g), _p(m), _p(v), p.numel(), float(beta1), float(beta2), float(eps),
+                           float(step_size), float(lr_wd), _dtype_code(p.dtype), _stream_ptr(p.device))
+    check(rc, "tt_adam_dense")
+    launch_counter["kernels"] += 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-tensor Adam
+# ---------------------------------------------------------------------------------------------------------
+
+def build_adam_chunks(ps: List[torch.Tensor], gs: List[torch.Tensor], ms: List[torch.Tensor],
+                      vs: List[torch.Tensor]) -> torch.Tensor:
+    """Device table int64[n_chunks,5] = (p, g, m, v, n) per chunk of <= sow_adam_chunk_elems() elements."""
+    lib = _lib.load()
+    ce = lib.sow_adam_chunk_elems()
+    rows = []
+    for p, g, m, v in zip(ps, gs, ms, vs):
+        _require_cuda(p, g, m, v)
+        if not (p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()):
+            raise SowB200Error("fused Adam needs contiguous p/g/m/v")
+        es = p.element_size()
+        n = p.numel()
+        for off in range(0, n, ce):
+            rows.append((p.data_ptr() + off * es, g.data_ptr() + off * es, m.data_ptr() + off * es,
+                         v.data_ptr() + off * es, min(ce, n - off)))
+    table = torch.from_numpy(np.asarray(rows, dtype=np.int64).reshape(-1, 5))
+    return table.to(ps[0].device, non_blocking=False)
+
+
+def adam_multi(chunks: torch.Tensor, dtype: torch.dtype, lr, beta1, beta2, eps, weight_decay, bc1, bc2, decoupled):
+    lib = _lib.load()
+    rc = lib.sow_adam_multi(_p(chunks), chunks.shape[0], float(lr), float(beta1), float(beta2), float(eps),
+                            float(weight_decay), float(bc1), float(bc2), 1 if decoupled else 0, _dtype_code(dtype),
+                            _stream_ptr(chunks.device))
+    check(rc, "sow_adam_multi")
+    launch_counter["kernels"] += 1

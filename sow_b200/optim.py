@@ -1,0 +1,225 @@
+"""Optimizers -- host-side mirrors of ``tn_gradient.optimizer.ttadam`` / ``ttsgd`` (reference files
+tn_gradient/optimizer/ttadam.py, ttsgd.py) plus the fused multi-tensor AdamW used for the factor group.
+
+TTAdam keeps the reference's state layout (``step``, ``exp_avg``, ``exp_avg_sq`` as TensorTrain objects after a
+step with "ranks", ``exp_avg_expr`` / ``exp_avg_sq_expr``) but executes each parameter's update as
+    order 2 : tt_adam_fused2 (reconstruct m, v + Adam + write padded/interleaved m', v')  ->  thin-QR + projection
+    order>2 : tt_matmul_rk chain + tt_deinterleave -> tt_adam_dense -> tt_interleave -> thin-QR + projection sweep
+instead of ~8 elementwise launches, two einsum reconstructions and two complete QRs.
+"""
+from __future__ import annotations
+
+import math
+from math import ceil
+from typing import Callable, Iterable, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import SowB200Error
+from .tt import TensorTrain
+
+
+class TTAdam(torch.optim.Optimizer):
+    """tn_gradient/optimizer/ttadam.py:10-117."""
+
+    def __init__(self, params: Iterable[nn.parameter.Parameter], lr: float = 1e-3,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0,
+                 amsgrad: bool = False, correct_bias: bool = True):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad,
+                        correct_bias=correct_bias)
+        super().__init__(params, defaults)
+
+    @torch.no_grad()
+    def step(self, closure: Callable = None):
+        loss = None
+        if closure is not None:
+            loss = closure()
+        for group in self.param_groups:
+            beta1, beta2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                grad = p.grad
+                if grad.is_sparse:
+                    raise RuntimeError("TTAdam does not support sparse gradients, please consider SparseAdam instead")
+                if not p.is_cuda:
+                    raise SowB200Error("TTAdam needs CUDA parameters (sm_100a kernels only, no CPU fallback)")
+                state = self.state[p]
+                if "step" not in state:
+                    state["step"] = 0
+                first = "exp_avg" not in state or "exp_avg_sq" not in state
+                state["step"] += 1
+                step_size = group["lr"]
+                if group["correct_bias"]:                                       # ttadam.py:97-100
+                    bc1 = 1.0 - beta1 ** state["step"]
+                    bc2 = 1.0 - beta2 ** state["step"]
+                    step_size = step_size * math.sqrt(bc2) / bc1
+                lr_wd = group["lr"] * group["weight_decay"] if group["weight_decay"] > 0.0 else 0.0
+                if "ranks" in group and grad.dim() == 2:
+                    self._tt_update(p, grad, state, list(group["ranks"]), first, beta1, beta2, group["eps"], step_size, lr_wd)
+                else:
+                    self._dense_update(p, grad, state, first, beta1, beta2, group["eps"], step_size, lr_wd)
+        return loss
+
+    @staticmethod
+    def _dense_update(p, grad, state, first, beta1, beta2, eps, step_size, lr_wd):
+        if first:
+            state["exp_avg"] = torch.zeros(grad.shape, dtype=torch.float32, device=grad.device)
+            state["exp_avg_sq"] = torch.zeros(grad.shape, dtype=torch.float32, device=grad.device)
+            state["exp_avg_expr"] = None
+            state["exp_avg_sq_expr"] = None
+        pd = p.data
+        if not pd.is_contiguous():
+            raise SowB200Error("TTAdam needs contiguous parameters")
+        g = grad if grad.dtype == pd.dtype else grad.to(pd.dtype)
+        ops.tt_adam_dense(pd, g, state["exp_avg"], state["exp_avg_sq"], beta1, beta2, eps, step_size, lr_wd)
+
+    @staticmethod
+    def _tt_update(p, grad, state, ranks, first, beta1, beta2, eps, step_size, lr_wd):
+        order = len(ranks) - 1
+        M, N = grad.shape
+        mm = ceil(M ** (1 / order))
+        nn_ = ceil(N ** (1 / order))
+        pd = p.data
+        if not pd.is_contiguous():
+            raise SowB200Error("TTAdam needs contiguous parameters")
+        g = grad if grad.dtype == pd.dtype else grad.to(pd.dtype)
+        if not first:
+            state["exp_avg_expr"] = state["exp_avg"].contract_expr          # ttadam.py:73,81
+            state["exp_avg_sq_expr"] = state["exp_avg_sq"].contract_expr
+        else:
+            state["exp_avg_expr"] = None
+            state["exp_avg_sq_expr"] = None
+        if order == 2:
+            r = ranks[1]
+            P = mm * nn_
+            cm = cv = None
+            if not first:
+                tm, tv = state["exp_avg"], state["exp_avg_sq"]
+                cm = (tm.cores[0].reshape(P, -1).contiguous(), tm.cores[1].reshape(-1, P).contiguous())
+                cv = (tv.cores[0].reshape(P, -1).contiguous(), tv.cores[1].reshape(-1, P).contiguous())
+            m_new, v_new = ops.tt_adam_fused2(pd, g, cm, cv, mm, nn_, beta1, beta2, eps, step_size, lr_wd, first)
+            L = torch.stack([m_new, v_new])                                  # (2, P, P): one batched sweep
+            if r > P:
+                raise RuntimeError(f"TT rank {r} exceeds the unfolding row count {P}")
+            Q = ops.thin_qr(L, r)
+            R = ops.project(L, Q)
+            for key, b in (("exp_avg", 0), ("exp_avg_sq", 1)):
+                tt = TensorTrain(list(ranks), (mm, mm), (nn_, nn_), device=pd.device)
+                tt.cores = [Q[b].reshape(1, mm, nn_, r), R[b].reshape(r, mm, nn_, 1)]
+                state[key] = tt
+            return
+        if first:
+            m = torch.zeros((M, N), dtype=torch.float32, device=pd.device)
+            v = torch.zeros((M, N), dtype=torch.float32, device=pd.device)
+        else:
+            m = state["exp_avg"].to_matrix((M, N))                           # ttadam.py:71-74
+            v = state["exp_avg_sq"].to_matrix((M, N))                        # ttadam.py:79-84 (clamp in kernel)
+        ops.tt_adam_dense(pd, g, m, v, beta1, beta2, eps, step_size, lr_wd)
+        state["exp_avg"] = TensorTrain.from_matrix(m, ranks=ranks, padding=True)      # ttadam.py:113-115
+        state["exp_avg_sq"] = TensorTrain.from_matrix(v, ranks=ranks, padding=True)
+
+
+class TTRAdam(torch.optim.Optimizer):
+    """Empty in the reference as well (tn_gradient/optimizer/ttadam.py:120-121)."""
+    pass
+
+
+class TTSGD(torch.optim.Optimizer):
+    """tn_gradient/optimizer/ttsgd.py:8-86: SGD whose gradient / momentum live in TT format.  Compression and
+    reconstruction use the CUDA kernels; the TT algebra in between is the (compat) PyTorch path of TensorTrain."""
+
+    def __init__(self, params, lr: float = 1e-3, momentum: float = 0.9, dampening: float = 0,
+                 weight_decay: float = 0, nesterov: bool = False):
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov)
+        super().__init__(params, defaults)
+
+    @torch.no_grad()
+    def step(self, closure: Callable = None):
+        loss = None
+        if closure is not None:
+            loss = closure()
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                grad = p.grad
+                grad_shape = grad.shape
+                if grad.is_sparse:
+                    raise RuntimeError("TTSGD does not support sparse gradients, please consider SparseAdam instead")
+                state = self.state[p]
+                if "step" not in state:
+                    state["step"] = 0
+                use_tt = "ranks" in group
+                d_p = TensorTrain.from_matrix(grad, ranks=list(group["ranks"]), padding=True) if use_tt else grad
+                if group["weight_decay"] != 0:
+                    if use_tt:
+                        raise RuntimeError("TTSGD: weight_decay with TT gradients is unsupported "
+                                           "(the reference calls a non-existent TensorTrain.add here, ttsgd.py:61)")
+                    d_p = d_p.add(p, alpha=group["weight_decay"])
+                if group["momentum"] != 0:
+                    if "momentum_buffer" not in state:
+                        buf = state["momentum_buffer"] = d_p.clone().detach()
+                    else:
+                        buf = state["momentum_buffer"]
+                        buf = group["momentum"] * buf + (1 - group["dampening"]) * d_p
+                    d_p = d_p + group["momentum"] * buf if group["nesterov"] else buf
+                if use_tt:
+                    d_p = d_p.to_matrix(grad_shape).to(p.dtype)
+                p.add_(-group["lr"] * d_p)
+                if group["weight_decay"] > 0.0:
+                    p.add_(p, alpha=(-group["lr"] * group["weight_decay"]))
+        return loss
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """Multi-tensor AdamW / Adam on one kernel launch per param group.
+
+    State layout is torch.optim.AdamW's (``state[p]["step"]`` tensor, ``exp_avg``, ``exp_avg_sq`` in the parameter
+    dtype), so ``reset_optimizer`` (scripts/utils/training_utils.py:257-277), which REBINDS those tensors and zeroes
+    ``step``, keeps working: pointers are re-resolved whenever a state tensor or gradient was rebound.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False,
+                 decoupled=True):
+        if amsgrad:
+            raise SowB200Error("FusedAdamW: amsgrad is not implemented")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, decoupled=decoupled)
+        super().__init__(params, defaults)
+        self._tables = {}
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            buckets = {}
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise SowB200Error("FusedAdamW needs CUDA parameters (no CPU fallback)")
+                st = self.state[p]
+                if len(st) == 0 or "exp_avg" not in st:
+                    st["step"] = torch.zeros((), dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                g = p.grad if p.grad.dtype == p.dtype else p.grad.to(p.dtype)
+                buckets.setdefault((int(st["step"]), p.dtype), []).append((p, g, st["exp_avg"], st["exp_avg_sq"]))
+            beta1, beta2 = group["betas"]
+            for (step, dtype), items in buckets.items():
+                sig = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()) for p, g, m, v in items)
+                key = (gi, dtype, len(items))
+                cached = self._tables.get(key)
+                if cached is None or cached[0] != sig:
+                    ps, gs, ms, vs = zip(*items)
+                    cached = (sig, ops.build_adam_chunks([p.data for p in ps], list(gs), list(ms), list(vs)))
+                    self._tables[key] = cached
+                ops.adam_multi(cached[1], dtype, group["lr"], beta1, beta2, group["eps"], group["weight_decay"],
+                               1.0 - beta1 ** step, 1.0 - beta2 ** step, group["decoupled"])
+        return loss

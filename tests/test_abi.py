@@ -1,0 +1,70 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sow_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sow_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|size_t|char\s*\*|const char\s*\*)\s+\*?\s*((?:sow|tt)_[a-z0-9_]+)\s*\(", text, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_symbols()
+    for must in ["sow_linear_fwd", "sow_linear_bwd_factors", "sow_linear_bwd_dx", "sow_merge_grouped", "sow_thin_qr",
+                 "tt_project", "tt_interleave", "tt_deinterleave", "tt_matmul_rk", "tt_adam_fused2", "tt_adam_dense",
+                 "sow_adam_multi", "sow_workspace_bytes", "sow_last_error", "sow_abi_version"]:
+        assert must in names, must
+
+
+def test_library_exports_every_declared_symbol():
+    from sow_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/sow_b200.h but not exported"
+
+
+def test_ctypes_signatures_cover_the_header():
+    from sow_b200 import _lib
+    assert sorted(_lib.SIGNATURES.keys()) == declared_symbols()
+    lib = _lib.load()
+    assert lib.sow_abi_version() == 1
+    assert lib.sow_rank_pad(50) == 64 and lib.sow_rank_pad(8) == 64 and lib.sow_rank_pad(65) == 128
+    assert lib.sow_workspace_bytes(_lib.OP_LINEAR_FWD, 4096, 1024, 2736, 50) >= 1024 * 64 * 2
+    assert lib.sow_merge_table_stride() % 128 == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from sow_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsow_b200.so")
+    with pytest.raises(_lib.SowB200Error, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from sow_b200 import ops
+    from sow_b200._lib import SowB200Error
+    x = torch.zeros(8, 16, dtype=torch.bfloat16)
+    with pytest.raises(SowB200Error, match="no CPU fallback"):
+        ops.linear_fwd(x, None, torch.zeros(16, 4, dtype=torch.bfloat16), torch.zeros(4, 8, dtype=torch.bfloat16), None, 1.0)
+    with pytest.raises(SowB200Error):
+        ops.thin_qr(torch.zeros(8, 4), 2)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under sow_b200/ or tn_gradient/ may reference it."""
+    for pkg in ("sow_b200", "tn_gradient"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "oracle" not in src.replace("sow_oracle_free", ""), os.path.join(dirpath, f)

@@ -1,0 +1,162 @@
+"""GPU parity: SoWLinear forward/backward through the public tn_gradient API (-> C ABI -> tcgen05 kernels) against
+the CPU oracle on the same inputs and against outputs of the unmodified reference (tests/golden/linear.npz).
+
+Tolerance (BASELINE.json north_star): rel. error <= 1e-2 vs an fp32/fp64 reference for bf16 compute."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import sow_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _layer_from_arrays(fin, fout, r, n_iter, scale, As, Bs, W, bias, dtype):
+    from tn_gradient.layer.sow import SoWLinear
+    layer = SoWLinear(fin, fout, bias=bias is not None, rank=r, n_iter=n_iter, scale=scale, init_method="normal",
+                      dtype=torch.float32)
+    with torch.no_grad():
+        for i in range(n_iter):
+            layer.downscale_weights[i].copy_(torch.from_numpy(As[i]))
+            layer.upscale_weights[i].copy_(torch.from_numpy(Bs[i]))
+        if bias is not None:
+            layer.bias.copy_(torch.from_numpy(bias))
+    if W is not None:
+        layer.acc_downweight = torch.nn.Parameter(torch.from_numpy(W).clone(), requires_grad=False)
+    layer.virtual_rank = min(fin, fout)
+    return layer.to("cuda", dtype)
+
+
+@pytest.mark.parametrize("case", ["f32_w_bias", "f32_now", "f32_niter2", "bf16_w", "bf16_now_bias"])
+def test_forward_backward_vs_reference_golden_and_oracle(golden_linear, case):
+    g = golden_linear
+    p = f"linear/{case}/"
+    n_iter = int(g[p + "n_iter"])
+    As = [g[p + f"A{i}"] for i in range(n_iter)]
+    Bs = [g[p + f"B{i}"] for i in range(n_iter)]
+    W = g[p + "W"] if (p + "W") in g else None
+    bias = g[p + "bias"] if (p + "bias") in g else None
+    scale = float(g[p + "scale"])
+    dtype = torch.bfloat16 if case.startswith("bf16") else torch.float32
+    fin, r = As[0].shape
+    fout = Bs[0].shape[1]
+    layer = _layer_from_arrays(fin, fout, r, n_iter, scale, As, Bs, W, bias, dtype)
+    x = torch.from_numpy(g[p + "x"]).to("cuda", dtype).requires_grad_(True)
+    dy = torch.from_numpy(g[p + "dy"]).to("cuda", dtype)
+    y = layer(x)
+    assert y.shape == dy.shape and y.dtype == dtype
+    y.backward(dy)
+    torch.cuda.synchronize()
+
+    # oracle on the same inputs (fp64 truth)
+    y_o = O.sow_linear_forward(g[p + "x"], W, As, Bs, bias, scale)
+    dx_o, dA_o, dB_o, db_o = O.sow_linear_backward(g[p + "dy"], g[p + "x"], W, As, Bs, scale)
+    got = {"y": y, "dx": x.grad}
+    want_o = {"y": y_o, "dx": dx_o}
+    for i in range(n_iter):
+        got[f"dA{i}"], got[f"dB{i}"] = layer.downscale_weights[i].grad, layer.upscale_weights[i].grad
+        want_o[f"dA{i}"], want_o[f"dB{i}"] = dA_o[i], dB_o[i]
+    if bias is not None:
+        got["dbias"], want_o["dbias"] = layer.bias.grad, db_o
+    for k in got:
+        a = got[k].detach().float().cpu().numpy()
+        assert rel_err(a, want_o[k]) < TOL, (k, "oracle", rel_err(a, want_o[k]))
+        assert rel_err(a, g[p + k]) < 1.5 * TOL, (k, "reference golden", rel_err(a, g[p + k]))
+
+
+SHAPES = [
+    # T, in, out, r, scale, W, bias   (BASELINE.json configs)
+    (4096, 1024, 1024, 50, 1.0, True, False),     # llama_350m q/k/v/o
+    (4096, 1024, 2736, 50, 1.0, True, False),     # llama_350m gate/up
+    (4096, 2736, 1024, 50, 1.0, True, False),     # llama_350m down
+    (4096, 512, 1376, 50, 1.0, False, False),     # llama_60m, pre-merge phase (no W)
+    (8192, 768, 3072, 8, 0.125, True, True),      # roberta-base intermediate.dense
+    (2048, 4096, 11008, 8, 0.125, True, False),   # llama_7b gate/up
+    (300, 264, 136, 50, 1.0, True, True),         # ragged everything
+    (1, 64, 64, 3, 2.0, True, False),             # single token
+    (130, 128, 128, 100, 1.0, True, False),       # rank > 64 (two tail k-blocks)
+]
+
+
+@pytest.mark.parametrize("T,fin,fout,r,scale,has_W,has_bias", SHAPES)
+def test_forward_backward_vs_oracle_at_baseline_shapes(T, fin, fout, r, scale, has_W, has_bias):
+    rng = np.random.default_rng(1234)
+    x = O.bf16_round(rng.standard_normal((T, fin), dtype=np.float32))
+    A = O.bf16_round(rng.standard_normal((fin, r), dtype=np.float32) * 0.05)
+    B = O.bf16_round(rng.standard_normal((r, fout), dtype=np.float32) * 0.05)
+    W = O.bf16_round(rng.standard_normal((fin, fout), dtype=np.float32) * 0.02) if has_W else None
+    bias = O.bf16_round(rng.standard_normal(fout, dtype=np.float32)) if has_bias else None
+    dy = O.bf16_round(rng.standard_normal((T, fout), dtype=np.float32))
+    layer = _layer_from_arrays(fin, fout, r, 1, scale, [A], [B], W, bias, torch.bfloat16)
+    xt = torch.from_numpy(x).to("cuda", torch.bfloat16).requires_grad_(True)
+    y = layer(xt)
+    y.backward(torch.from_numpy(dy).to("cuda", torch.bfloat16))
+    torch.cuda.synchronize()
+    # fp32 BLAS oracle is enough here (error budget 1e-2) and keeps the CPU side to seconds
+    y_o = O.sow_linear_forward(x, W, [A], [B], bias, scale, dtype=np.float32)
+    dx_o, dA_o, dB_o, db_o = O.sow_linear_backward(dy, x, W, [A], [B], scale, dtype=np.float32)
+    assert rel_err(y.detach().float().cpu().numpy(), y_o) < TOL
+    assert rel_err(xt.grad.float().cpu().numpy(), dx_o) < TOL
+    assert rel_err(layer.downscale_weights[0].grad.float().cpu().numpy(), dA_o[0]) < TOL
+    assert rel_err(layer.upscale_weights[0].grad.float().cpu().numpy(), dB_o[0]) < TOL
+    if has_bias:
+        assert rel_err(layer.bias.grad.float().cpu().numpy(), db_o) < TOL
+
+
+def test_linearity_and_scale_property_at_full_size():
+    """Size-independent properties at a BASELINE shape: y is linear in x and affine in `scale`."""
+    from tn_gradient.layer.sow import SoWLinear
+    torch.manual_seed(0)
+    layer = SoWLinear(1024, 2736, bias=False, rank=50, init_method="normal", dtype=torch.bfloat16, device="cuda")
+    layer.acc_downweight = torch.nn.Parameter((torch.randn(1024, 2736, device="cuda") * 0.02).bfloat16(), requires_grad=False)
+    with torch.no_grad():
+        layer.upscale_weights[0].normal_(0, 0.05)
+    x1 = torch.randn(16, 256, 1024, device="cuda").bfloat16()
+    x2 = torch.randn(16, 256, 1024, device="cuda").bfloat16()
+    with torch.no_grad():
+        y1, y2, y12 = layer(x1).float(), layer(x2).float(), layer(x1 + x2).float()
+        e_lin = float((y12 - (y1 + y2)).norm() / y12.norm())
+        layer.scale = 0.0
+        y_base = layer(x1).float()
+        layer.scale = 2.0
+        y_two = layer(x1).float()
+        e_aff = float(((y_two - y_base) - 2.0 * (y1 - y_base)).norm() / (y_two - y_base).norm())
+    assert e_lin < 2e-2 and e_aff < 2e-2, (e_lin, e_aff)
+
+
+def test_frozen_factors_and_no_input_grad():
+    from tn_gradient.layer.sow import SoWLinear
+    layer = SoWLinear(128, 128, bias=False, rank=8, init_method="normal", dtype=torch.bfloat16, device="cuda")
+    layer.upscale_weights[0].requires_grad_(False)
+    x = torch.randn(64, 128, device="cuda", dtype=torch.bfloat16)      # x does not require grad
+    layer(x).sum().backward()
+    assert layer.downscale_weights[0].grad is not None and layer.upscale_weights[0].grad is None
+
+
+def test_activation_checkpointing_reentrant_and_not():
+    from torch.utils.checkpoint import checkpoint
+    from tn_gradient.layer.sow import SoWLinear
+    torch.manual_seed(0)
+    layer = SoWLinear(256, 256, bias=True, rank=8, init_method="normal", dtype=torch.bfloat16, device="cuda")
+    with torch.no_grad():
+        layer.upscale_weights[0].normal_(0, 0.05)
+        layer.bias.normal_()
+    x = torch.randn(4, 32, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    layer(x).float().pow(2).sum().backward()
+    ref = [x.grad.clone(), layer.downscale_weights[0].grad.clone(), layer.bias.grad.clone()]
+    for reentrant in (False, True):
+        x.grad = None
+        layer.zero_grad()
+        checkpoint(layer, x, use_reentrant=reentrant).float().pow(2).sum().backward()
+        for a, b in zip([x.grad, layer.downscale_weights[0].grad, layer.bias.grad], ref):
+            assert torch.equal(a, b)
+
+
+def test_unsupported_feature_size_fails_loudly():
+    from sow_b200 import SowB200Error
+    from tn_gradient.layer.sow import SoWLinear
+    layer = SoWLinear(100, 5461 - 5461 % 2 + 1, bias=False, rank=4, init_method="normal", dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(SowB200Error, match="multiples of 8"):
+        layer(torch.randn(4, 100, device="cuda", dtype=torch.bfloat16))
