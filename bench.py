@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the SoW training hot path on B200 (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): SoW Llama-350M r=50 bf16 pre-training tokens/s (reference definition, simple_train.py:
+609,680-690: global non-pad tokens per optimizer update / time per update), synthetic tokens, random-init weights.
+One "step" = one optimizer update of the training loop (forward, backward, gradient averaging, fused AdamW) in
+steady state (after >= 1 merge, dense W present).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama_350m")
+    ap.add_argument("--rank", type=int, default=50)
+    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step")
+    ap.add_argument("--seq", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused-optimizer", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure Python
+    and /root/reference does not exist on the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.cpu_trainer import time_cpu_training
+    sample_batch = 2
+    t0 = time.time()
+    res = time_cpu_training(args.model, args.rank, batch=sample_batch, seq_len=args.seq, steps=args.steps,
+                            warmup=max(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": "train_tokens_per_s", "value": res["tokens_per_s"], "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, args.warmup),
+        "ms_per_step": res["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} SoW r={args.rank} pre-training step, seq {args.seq}, steady state after 1 merge",
+                   "sample": f"{sample_batch} x {args.seq} tokens per step on host cores (fp32, eager torch ops of the reference)"},
+        "cpu_baseline": {"value": res["tokens_per_s"], "unit": "tokens/s", "cores": res["threads"], "kind": "port",
+                         "sample": f"{args.steps} steps of {sample_batch}x{args.seq} tokens, merge in warm-up"},
+        "e2e": {"value": res["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sow_b200 import ops
+    from sow_b200.trainer import LLAMA_SHAPES, SoWTrainer, TrainConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    peaks = load_peaks()
+
+    cfg = TrainConfig(model=args.model, rank=args.rank, seq_len=args.seq, batch_size=args.batch,
+                      fused_optimizer=not args.no_fused_optimizer)
+    trainer = SoWTrainer(cfg, device)
+    B, S = args.batch, args.seq
+    n_batches = 8
+    gen = torch.Generator().manual_seed(1234 + rank)                      # per-rank stream
+    host_batches = [torch.randint(1, 32000, (B, S), generator=gen, dtype=torch.int64).pin_memory() for _ in range(n_batches)]
+    dev_batches = [b.to(device) for b in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: W steps, the first followed by a merge so that the timed steps see a dense W --------------
+    W = max(args.warmup, 3)
+    for i in range(W):
+        loss = trainer.step(dev_batches[i % n_batches])
+        if i == 0:
+            trainer.merge()
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM --------------------------------------------------------------
+    K = args.steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_counter["kernels"]
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = trainer.step(dev_batches[i % n_batches])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_counter["kernels"] - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms)
+    tokens_per_step = B * S * world
+    value = tokens_per_step * K / (ms_max / 1e3)
+    final_loss = float(loss)
+
+    # ---- timed region 2: end to end through the public API with HOST buffers -------------------------------
+    barrier()
+    e0.record()
+    for i in range(K):
+        ids = host_batches[i % n_batches].to(device, non_blocking=True)   # H2D of this step's inputs (pinned)
+        loss = trainer.step(ids)
+        _ = loss.item()                                                    # D2H of the step's result
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = tokens_per_step * K / (float(ms2) / 1e3)
+
+    # ---- instrumented pass: CUDA events around every kernel of each class (not part of `value`) -------------
+    ops.profile_enable(True)
+    for i in range(args.profile_steps):
+        trainer.step(dev_batches[i % n_batches])
+    torch.cuda.synchronize()
+    kern = {}
+    for k in ops.PROF_CLASSES:
+        tms, work, n = ops.profile_read(k)
+        kern[k] = {"ms_total": tms, "work": work, "launches": n}
+    ops.profile_enable(False)
+    # merge event, timed alone (burst peak)
+    torch.cuda.synchronize()
+    ops.profile_enable(True)
+    trainer.merge()
+    torch.cuda.synchronize()
+    mg_ms, mg_bytes, mg_n = ops.profile_read("merge")
+    ops.profile_enable(False)
+
+    # dominant kernel: the fused SoW GEMM (forward y and backward dX are the same kernel template)
+    gemm_ms = kern["gemm_fwd"]["ms_total"] + kern["gemm_dx"]["ms_total"]
+    gemm_flops = kern["gemm_fwd"]["work"] + kern["gemm_dx"]["work"]
+    gemm_n = kern["gemm_fwd"]["launches"] + kern["gemm_dx"]["launches"]
+    achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    peak_tf = peaks["bf16_tflops_sustained"]
+    step_ms = ms_max / K
+    roofline = {
+        "kernel": "sow_gemm_kernel<BN=256> (y = x.W + t.B and dX = dY.W^T + dt.A^T, tcgen05/TMEM/TMA)",
+        "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+        "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+        "launches_timed": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
+        "share_of_step": (gemm_ms / max(args.profile_steps, 1)) / step_ms,
+    }
+    merge_gbs = mg_bytes / (mg_ms / 1e3) / 1e9 if mg_ms > 0 else 0.0
+    extra_kernels = {
+        "merge": {"bound": "hbm", "achieved": merge_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "frac": merge_gbs / peaks["hbm_gbs"], "ms": mg_ms, "algorithmic_bytes": mg_bytes, "launches": mg_n},
+    }
+    for k in ("gemm_skinny", "gemm_splitk", "adam"):
+        d = kern[k]
+        if d["ms_total"] > 0:
+            rate = d["work"] / (d["ms_total"] / 1e3)
+            extra_kernels[k] = {"ms_per_step": d["ms_total"] / args.profile_steps, "launches_per_step": d["launches"] / args.profile_steps,
+                                "achieved": rate / (1e9 if k == "adam" else 1e12), "unit": "GB/s" if k == "adam" else "TFLOP/s"}
+    extra_kernels["gemm_fwd_ms_per_step"] = kern["gemm_fwd"]["ms_total"] / args.profile_steps
+    extra_kernels["gemm_dx_ms_per_step"] = kern["gemm_dx"]["ms_total"] / args.profile_steps
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port of the reference's CPU path on the host cores ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_trainer import time_cpu_training
+        res = time_cpu_training(args.model, args.rank, batch=2, seq_len=S, steps=3, warmup=1)
+        cpu_baseline = {"value": res["tokens_per_s"], "unit": "tokens/s", "cores": res["threads"], "kind": "port",
+                        "sample": f"3 steps of 2x{S} tokens ({args.model} SoW r={args.rank}, fp32, merge in warm-up), "
+                                  f"{res['sec_per_step']:.2f} s/step"}
+
+    if rank == 0:
+        shp = LLAMA_SHAPES[args.model]
+        line = {
+            "metric": "train_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": f"{args.model} (h={shp['hidden_size']}, ff={shp['intermediate_size']}, L={shp['num_hidden_layers']}) "
+                            f"SoW rank {args.rank} bf16 pre-training, steady state after 1 merge (dense W), "
+                            f"fwd+bwd+grad-avg+fused AdamW per step",
+                "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "tokens_per_step": tokens_per_step,
+                "parallelism": f"dp{world}", "l2": "working set per step (>1 GB weights+activations) exceeds the 126 MB L2; no flush needed",
+                "optimizer": "FusedAdamW (sow_adam_multi)" if cfg.fused_optimizer else "torch.optim.AdamW",
+            },
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "kernels": extra_kernels,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "loss": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,15 @@ enum sowb_op {
 int sow_abi_version(void);
 const char* sow_last_error(void);
 
+/*
+ * Live per-kernel timing for bench.py's roofline: while enabled, every launch of the classes below is bracketed
+ * by CUDA events on the launching stream.  sow_profile_read sums elapsed milliseconds, algorithmic work (flops for
+ * GEMM classes, bytes for merge / Adam) and the launch count of one class.  Classes: 0 forward GEMM (y), 1 dX GEMM,
+ * 2 skinny GEMMs (t, dt), 3 split-K GEMMs (dA, dB), 4 grouped merge, 5 multi-tensor Adam.
+ */
+int sow_profile_enable(int on);
+int sow_profile_read(int klass, double* total_ms, double* total_work, int64_t* launches);
+
 /* Bytes of scratch the op needs for the given problem (T tokens, in/out features, rank r). */
 size_t sow_workspace_bytes(int op, int64_t T, int in, int out, int r);
 
@@ -160,6 +169,10 @@ int sow_adam_chunk_elems(void);
 int sow_adam_multi(const void* chunks_dev, int n_chunks, double lr, double beta1, double beta2, double eps,
                    double weight_decay, double bias_correction1, double bias_correction2, int decoupled, int dtype,
                    void* stream);
+/* same, with the total element count of the table for the profiler's byte accounting */
+int sow_adam_multi_ex(const void* chunks_dev, int n_chunks, int64_t total_elems, double lr, double beta1, double beta2,
+                      double eps, double weight_decay, double bias_correction1, double bias_correction2, int decoupled,
+                      int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,6 +46,8 @@ _d = ctypes.c_double
 SIGNATURES = {
     "sow_abi_version": (_i, []),
     "sow_last_error": (ctypes.c_char_p, []),
+    "sow_profile_enable": (_i, [_i]),
+    "sow_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "sow_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),
     "sow_rank_pad": (_i, [_i]),
     "sow_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
@@ -61,6 +63,7 @@ SIGNATURES = {
     "tt_adam_fused2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i, _vp]),
     "tt_adam_dense": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _vp]),
     "sow_adam_chunk_elems": (_i, []),
+    "sow_adam_multi_ex": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _d, _d, _i, _i, _vp]),
     "sow_adam_multi": (_i, [_vp, _i, _d, _d, _d, _d, _d, _d, _d, _i, _i, _vp]),
 }
 

@@ -117,9 +117,20 @@ extern "C" {
 
 int sow_adam_chunk_elems(void) { return 32768; }
 
+int sow_adam_multi_ex(const void* chunks_dev, int n_chunks, int64_t total_elems, double lr, double beta1, double beta2,
+                      double eps, double weight_decay, double bias_correction1, double bias_correction2, int decoupled,
+                      int dtype, void* stream_);
+
 int sow_adam_multi(const void* chunks_dev, int n_chunks, double lr, double beta1, double beta2, double eps,
                    double weight_decay, double bias_correction1, double bias_correction2, int decoupled, int dtype,
                    void* stream_) {
+  return sow_adam_multi_ex(chunks_dev, n_chunks, 0, lr, beta1, beta2, eps, weight_decay, bias_correction1,
+                           bias_correction2, decoupled, dtype, stream_);
+}
+
+int sow_adam_multi_ex(const void* chunks_dev, int n_chunks, int64_t total_elems, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, double bias_correction1, double bias_correction2, int decoupled,
+                      int dtype, void* stream_) {
   if (n_chunks <= 0) return SOWB_OK;
   SOWB_REQUIRE(chunks_dev != nullptr, "sow_adam_multi: null chunk table");
   SOWB_REQUIRE(bias_correction1 > 0.0 && bias_correction2 > 0.0, "sow_adam_multi: bias corrections must be positive");
@@ -136,6 +147,8 @@ int sow_adam_multi(const void* chunks_dev, int n_chunks, double lr, double beta1
   h.step_size = float(lr / bias_correction1);
   h.inv_sqrt_bc2 = float(1.0 / sqrt(bias_correction2));
   h.decoupled = decoupled;
+  // algorithmic bytes: p, m, v read+written, g read = 7 accesses of the element size
+  ProfileScope prof(stream, PROF_ADAM, 7.0 * double(total_elems) * (dtype == SOWB_BF16 ? 2 : 4));
   if (dtype == SOWB_BF16)
     adam_multi_bf16_kernel<<<n_chunks, 256, 0, stream>>>(static_cast<const AdamChunk*>(chunks_dev), h);
   else if (dtype == SOWB_F32)

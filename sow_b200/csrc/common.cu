@@ -3,6 +3,7 @@
 #include <mutex>
 #include <string.h>
 #include <unordered_map>
+#include <vector>
 
 namespace sowb {
 
@@ -133,9 +134,71 @@ int make_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint6
   return SOWB_OK;
 }
 
+// ---- live profiling --------------------------------------------------------------------------------
+struct ProfRecord {
+  cudaEvent_t a, b;
+  int klass;
+  double work;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+
+bool profile_enabled() { return g_prof_on; }
+
+ProfileScope::ProfileScope(cudaStream_t s, int k, double w) : stream(s), klass(k), work(w) {
+  if (!g_prof_on) return;
+  if (cudaEventCreate(&start) != cudaSuccess) {
+    start = nullptr;
+    return;
+  }
+  cudaEventRecord(start, stream);
+}
+ProfileScope::~ProfileScope() {
+  if (start == nullptr) return;
+  cudaEvent_t end;
+  if (cudaEventCreate(&end) != cudaSuccess) {
+    cudaEventDestroy(start);
+    return;
+  }
+  cudaEventRecord(end, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back({start, end, klass, work});
+}
+
 }  // namespace sowb
 
 extern "C" {
+int sow_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(sowb::g_prof_mu);
+  for (auto& r : sowb::g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  sowb::g_prof.clear();
+  sowb::g_prof_on = on != 0;
+  return SOWB_OK;
+}
+int sow_profile_read(int klass, double* total_ms, double* total_work, int64_t* launches) {
+  std::lock_guard<std::mutex> lk(sowb::g_prof_mu);
+  double ms = 0, work = 0;
+  int64_t n = 0;
+  for (auto& r : sowb::g_prof) {
+    if (r.klass != klass) continue;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return sowb::set_error(SOWB_ECUDA, "sow_profile_read: %s", cudaGetErrorString(e));
+    float t = 0;
+    e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) return sowb::set_error(SOWB_ECUDA, "sow_profile_read: %s", cudaGetErrorString(e));
+    ms += t;
+    work += r.work;
+    ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_work) *total_work = work;
+  if (launches) *launches = n;
+  return SOWB_OK;
+}
 int sow_abi_version(void) { return 1; }
 const char* sow_last_error(void) { return sowb::g_err; }
 }

@@ -37,6 +37,29 @@ int require_sm100();
 int make_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                        uint32_t box_inner, uint32_t box_outer, int elem_bytes);
 
+// ------------------------------------------------------------------------------------------------
+// Live per-kernel timing (bench.py roofline): when enabled, launches are bracketed by CUDA events recorded on the
+// launching stream; sow_profile_read() sums elapsed time / algorithmic work per kernel class.
+// ------------------------------------------------------------------------------------------------
+enum ProfClass : int {
+  PROF_GEMM_FWD = 0,     // y  = x.W + t.B          (flops)
+  PROF_GEMM_DX = 1,      // dX = dY.W^T + dt.A^T    (flops)
+  PROF_GEMM_SKINNY = 2,  // t = x.A, dt = dY.B^T    (flops)
+  PROF_GEMM_SPLITK = 3,  // dA, dB                  (flops)
+  PROF_MERGE = 4,        // grouped merge           (bytes)
+  PROF_ADAM = 5,         // multi-tensor Adam       (bytes)
+  PROF_NUM = 6,
+};
+bool profile_enabled();
+struct ProfileScope {
+  cudaStream_t stream;
+  cudaEvent_t start = nullptr;
+  int klass;
+  double work;
+  ProfileScope(cudaStream_t s, int klass, double work);
+  ~ProfileScope();
+};
+
 __host__ __device__ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 __host__ __device__ static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }

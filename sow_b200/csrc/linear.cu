@@ -80,7 +80,7 @@ struct Operand {
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const Operand& A, const Operand& B, const Operand* A2, const Operand* B2, void* C_bf16,
                        float* C_f32, int ldc, int M, int N, int K, int K2, float alpha, const void* bias,
-                       bool split_k, cudaStream_t stream) {
+                       bool split_k, cudaStream_t stream, int prof_class = PROF_GEMM_SKINNY) {
   using S = GemmSmem<BN>;
   CUtensorMap tmA, tmB, tmA2, tmB2, tmC;
   int rc;
@@ -127,6 +127,8 @@ static int launch_gemm(const Operand& A, const Operand& B, const Operand* A2, co
   auto kern = sow_gemm_kernel<BN, A_MN, B_MN, EPI>;
   SOWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   const int grid = total < sms ? total : sms;
+  // algorithmic flops: un-padded contraction lengths
+  ProfileScope prof(stream, prof_class, 2.0 * double(M) * double(N) * (double(K) + double(K2)));
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tmA, tmB, tmA2, tmB2, tmC, p);
   SOWB_CHECK_CUDA(cudaGetLastError());
   return SOWB_OK;
@@ -197,10 +199,11 @@ int sow_linear_fwd(const void* x, const void* W, const void* A, const void* B, c
   if (W != nullptr) {
     Operand opWMN{W, uint64_t(in), uint64_t(out), uint64_t(out)};  // [K=in rows, N=out cols]
     rc = launch_gemm<256, false, true, EPI_BF16_TMA>(opX, opWMN, &opT, &opBMN, y, nullptr, out, static_cast<int>(T),
-                                                     out, in, r_pad, 1.0f, bias, false, stream);
+                                                     out, in, r_pad, 1.0f, bias, false, stream, PROF_GEMM_FWD);
   } else {
     rc = launch_gemm<256, false, true, EPI_BF16_TMA>(opT, opBMN, nullptr, nullptr, y, nullptr, out,
-                                                     static_cast<int>(T), out, r_pad, 0, 1.0f, bias, false, stream);
+                                                     static_cast<int>(T), out, r_pad, 0, 1.0f, bias, false, stream,
+                                                     PROF_GEMM_FWD);
   }
   return rc;
 }
@@ -232,13 +235,13 @@ int sow_linear_bwd_factors(const void* dy, const void* x, const void* t, const v
   // dB^T [out, r_pad] = dY^T . t   (both operands MN-major; K = T, split-K with fp32 red.add)
   Operand opT{t, uint64_t(T), uint64_t(r_pad), uint64_t(r_pad)};
   rc = launch_gemm<64, true, true, EPI_F32_ATOMIC>(opDY, opT, nullptr, nullptr, nullptr, accB, r_pad, out, r_pad,
-                                                   static_cast<int>(T), 0, 1.0f, nullptr, true, stream);
+                                                   static_cast<int>(T), 0, 1.0f, nullptr, true, stream, PROF_GEMM_SPLITK);
   if (rc) return rc;
   // dA [in, r_pad] = x^T . dt
   Operand opX{x, uint64_t(T), uint64_t(in), uint64_t(in)};
   Operand opDT{dt, uint64_t(T), uint64_t(r_pad), uint64_t(r_pad)};
   rc = launch_gemm<64, true, true, EPI_F32_ATOMIC>(opX, opDT, nullptr, nullptr, nullptr, accA, r_pad, in, r_pad,
-                                                   static_cast<int>(T), 0, 1.0f, nullptr, true, stream);
+                                                   static_cast<int>(T), 0, 1.0f, nullptr, true, stream, PROF_GEMM_SPLITK);
   if (rc) return rc;
   {
     const int nA_blocks = ceil_div(in * r, 1024);
@@ -281,10 +284,12 @@ int sow_linear_bwd_dx(const void* dy, const void* dt, const void* W, const void*
     Operand opDY{dy, uint64_t(T), uint64_t(out), uint64_t(out)};
     Operand opWK{W, uint64_t(in), uint64_t(out), uint64_t(out)};
     rc = launch_gemm<256, false, false, EPI_BF16_TMA>(opDY, opWK, &opDT, &opApadK, dx, nullptr, in,
-                                                      static_cast<int>(T), in, out, r_pad, 1.0f, nullptr, false, stream);
+                                                      static_cast<int>(T), in, out, r_pad, 1.0f, nullptr, false, stream,
+                                                      PROF_GEMM_DX);
   } else {
     rc = launch_gemm<256, false, false, EPI_BF16_TMA>(opDT, opApadK, nullptr, nullptr, dx, nullptr, in,
-                                                      static_cast<int>(T), in, r_pad, 0, 1.0f, nullptr, false, stream);
+                                                      static_cast<int>(T), in, r_pad, 0, 1.0f, nullptr, false, stream,
+                                                      PROF_GEMM_DX);
   }
   return rc;
 }

@@ -30,7 +30,8 @@ constexpr int kMgWBytes = kMgBM * kMgBN * 2;        // 32 KB
 constexpr int kMgBBytes = 64 * kMgBN * 2;           // 16 KB
 constexpr int kMgABytes = kMgBM * 64 * 2;           // 16 KB
 constexpr int kMgSlotBytes = kMgWBytes + kMgBBytes + kMgABytes;
-constexpr int kMgSmemTotal = 1024 + kMgSlots * kMgSlotBytes + 256;
+constexpr int kMgMaxEntries = 2048;   // per launch (host splits longer tables)
+constexpr int kMgSmemTotal = 1024 + kMgSlots * kMgSlotBytes + 256 + kMgMaxEntries * 4;
 constexpr int kMgThreads = 288;
 constexpr uint32_t kMgTmemCols = 256;
 
@@ -46,13 +47,11 @@ struct alignas(128) MergeDevEntry {
   int has_prev;
 };
 
-__device__ __forceinline__ int find_entry(const MergeDevEntry* __restrict__ tab, int n, int tile) {
-  int lo = 0, hi = n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (tab[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
-  }
-  return lo;
+// Tiles are visited in increasing order by every role, so the entry index only ever moves forward: walk it.
+// `ends` (smem) holds tile_begin + #tiles of every entry, staged once per CTA.
+__device__ __forceinline__ int advance_entry(const int* __restrict__ ends, int ei, int tile) {
+  while (tile >= ends[ei]) ++ei;
+  return ei;
 }
 
 __global__ void __launch_bounds__(kMgThreads, 1)
@@ -65,8 +64,10 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
   uint64_t* tfull_bar = bars + 2 * kMgSlots;    // [2]
   uint64_t* tempty_bar = bars + 2 * kMgSlots + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMgSlots + 4);
+  int* ends = reinterpret_cast<int*>(smem + kMgSlots * kMgSlotBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < n_entries; i += kMgThreads) ends[i] = tab[i].tile_begin + tab[i].m_tiles * tab[i].n_tiles;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMgSlots; ++i) {
       mbar_init(&full_bar[i], 129);
@@ -91,16 +92,31 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
     // ===================== producer group =====================
     const int pt = threadIdx.x - 128;  // 0..127
     const MergeDevEntry* last_e = nullptr;
-    int slot = 0;
+    int slot = 0, ei = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const MergeDevEntry* e = &tab[find_entry(tab, n_entries, tile)];
+      ei = advance_entry(ends, ei, tile);
+      const MergeDevEntry* e = &tab[ei];
       const int local = tile - e->tile_begin;
       const int m0 = (local / e->n_tiles) * kMgBM;
       const int n0 = (local % e->n_tiles) * kMgBN;
       uint8_t* sW = smem + slot * kMgSlotBytes;
       uint8_t* sB = sW + kMgWBytes;
       uint8_t* sA = sB + kMgBBytes;
+      // issue the A loads BEFORE waiting for the slot: their latency overlaps the wait
+      const __nv_bfloat16* A = e->A;
+      const int r = e->r, lda = e->lda, rows = min(kMgBM, e->in - m0);
+      const bool vec = (lda == r) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((r & 7) == 0 || (m0 * r) % 8 == 0);
+      uint4 av[8];
+      const int nvec = (rows * r) >> 3;                 // whole 8-element groups of the contiguous [rows x r] block
+      if (vec) {
+        const uint4* src = reinterpret_cast<const uint4*>(A + static_cast<int64_t>(m0) * r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int v = pt + 128 * j;
+          if (v < nvec) av[j] = __ldg(src + v);
+        }
+      }
       mbar_wait(&empty_bar[slot], phase ^ 1);
       if (pt == 0) {
         if (e != last_e) {
@@ -116,17 +132,49 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
         tma_load_2d(sB, &e->tmB, &full_bar[slot], n0, 0);
         tma_load_2d(sB + 8192, &e->tmB, &full_bar[slot], n0 + 64, 0);
       }
-      // gather A[m0 : m0+128, 0 : r] into the K-major swizzled tile, zero padded to 64 columns
-      {
-        const __nv_bfloat16* A = e->A;
-        const int r = e->r, lda = e->lda, rows = min(kMgBM, e->in - m0);
+      // A[m0 : m0+128, 0 : r] -> K-major swizzled tile, zero padded to 64 columns
+      auto put = [&](int row, int col, __nv_bfloat16 v) {
+        *reinterpret_cast<__nv_bfloat16*>(sA + row * 128 + (((col >> 3) ^ (row & 7)) << 4) + (col & 7) * 2) = v;
+      };
+      if (vec) {
+        // 1) zero the padding columns r..63 (and rows beyond the matrix edge), 16 B at a time where possible
+        for (int idx = pt; idx < kMgBM * 8; idx += 128) {
+          const int row = idx >> 3, chunk = idx & 7;
+          if (row >= rows || chunk * 8 >= r)
+            *reinterpret_cast<uint4*>(sA + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+          else if (chunk * 8 + 8 > r)
+            for (int c = r; c < chunk * 8 + 8; ++c) put(row, c, __float2bfloat16(0.f));
+        }
+        // 2) scatter the prefetched 16-byte groups (a group may straddle two rows when r % 8 != 0)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int v = pt + 128 * j;
+          if (v < nvec) {
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&av[j]);
+            int e0 = v * 8;
+            int row = e0 / r, col = e0 - row * r;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              put(row, col, h[q]);
+              if (++col == r) {
+                col = 0;
+                ++row;
+              }
+            }
+          }
+        }
+        for (int e1 = nvec * 8 + pt; e1 < rows * r; e1 += 128) {   // tail elements of the block
+          const int row = e1 / r, col = e1 - row * r;
+          put(row, col, A[static_cast<int64_t>(m0) * r + e1]);
+        }
+      } else {
         const int col = pt & 63;
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < 64; ++j) {
           const int row = (pt >> 6) + 2 * j;
           __nv_bfloat16 v = __float2bfloat16(0.f);
           if (col < r && row < rows) v = A[static_cast<int64_t>(m0 + row) * lda + col];
-          *reinterpret_cast<__nv_bfloat16*>(sA + row * 128 + (((col >> 3) ^ (row & 7)) << 4) + (col & 7) * 2) = v;
+          put(row, col, v);
         }
       }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -139,10 +187,11 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
   } else if (warp == 8 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(1, kMgBM, kMgBN, 0, 1);
-    int slot = 0, acc = 0;
+    int slot = 0, acc = 0, ei = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const MergeDevEntry* e = &tab[find_entry(tab, n_entries, tile)];
+      ei = advance_entry(ends, ei, tile);
+      const MergeDevEntry* e = &tab[ei];
       const int ksteps = (e->r + 15) >> 4;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       mbar_wait(&full_bar[slot], phase);
@@ -168,12 +217,13 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
     // ===================== epilogue group =====================
     const int et = threadIdx.x;
     const int row = warp * 32 + lane;
-    int slot = 0, acc = 0;
+    int slot = 0, acc = 0, ei = 0;
     uint32_t phase = 0, acc_phase = 0;
     int prev_slot = -1;
     const MergeDevEntry* last_e = nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const MergeDevEntry* e = &tab[find_entry(tab, n_entries, tile)];
+      ei = advance_entry(ends, ei, tile);
+      const MergeDevEntry* e = &tab[ei];
       const int local = tile - e->tile_begin;
       const int m0 = (local / e->n_tiles) * kMgBM;
       const int n0 = (local % e->n_tiles) * kMgBN;
@@ -319,10 +369,15 @@ int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* t
       host.push_back(d);
     }
     if (host.empty()) break;
+    if (host.size() > size_t(kMgMaxEntries))
+      return set_error(SOWB_EINVAL, "sow_merge_grouped: at most %d entries per call", kMgMaxEntries);
     SOWB_CHECK_CUDA(cudaMemcpyAsync(table_dev, host.data(), host.size() * sizeof(MergeDevEntry),
                                     cudaMemcpyHostToDevice, stream));
     const int sms = num_sms();
     const int grid = tiles < sms ? tiles : sms;
+    double bytes = 0;   // algorithmic: W read (if any) + W write + A + B
+    for (const auto& d : host) bytes += 2.0 * d.in * d.out * (1 + d.has_prev) + 2.0 * d.r * (double(d.in) + d.out);
+    ProfileScope prof(stream, PROF_MERGE, bytes);
     sow_merge_kernel<<<grid, kMgThreads, kMgSmemTotal, stream>>>(static_cast<const MergeDevEntry*>(table_dev),
                                                                  static_cast<int>(host.size()), tiles);
     SOWB_CHECK_CUDA(cudaGetLastError());

@@ -106,7 +106,7 @@ def linear_bwd_factors(dy, x, t, B, scale: float, want_dbias: bool, fin: int):
     rc = lib.sow_linear_bwd_factors(_p(dy), _p(x), _p(t), _p(B), _p(dt), _p(dA), _p(dB), _p(dbias), T, fin, fout, r,
                                     float(scale), SOWB_BF16, _p(ws), ws.numel(), _stream_ptr(dev))
     check(rc, "sow_linear_bwd_factors")
-    launch_counter["kernels"] += 5 + (2 if want_dbias else 0)
+    launch_counter["kernels"] += 4 + (2 if want_dbias else 0)
     return dt, dA, dB, dbias
 
 
@@ -295,14 +295,34 @@ def build_adam_chunks(ps: List[torch.Tensor], gs: List[torch.Tensor], ms: List[t
         for off in range(0, n, ce):
             rows.append((p.data_ptr() + off * es, g.data_ptr() + off * es, m.data_ptr() + off * es,
                          v.data_ptr() + off * es, min(ce, n - off)))
-    table = torch.from_numpy(np.asarray(rows, dtype=np.int64).reshape(-1, 5))
-    return table.to(ps[0].device, non_blocking=False)
+    table = torch.from_numpy(np.asarray(rows, dtype=np.int64).reshape(-1, 5)).to(ps[0].device, non_blocking=False)
+    table._sow_total_elems = int(sum(p.numel() for p in ps))
+    return table
 
 
 def adam_multi(chunks: torch.Tensor, dtype: torch.dtype, lr, beta1, beta2, eps, weight_decay, bc1, bc2, decoupled):
     lib = _lib.load()
-    rc = lib.sow_adam_multi(_p(chunks), chunks.shape[0], float(lr), float(beta1), float(beta2), float(eps),
-                            float(weight_decay), float(bc1), float(bc2), 1 if decoupled else 0, _dtype_code(dtype),
-                            _stream_ptr(chunks.device))
+    total = getattr(chunks, "_sow_total_elems", 0)
+    rc = lib.sow_adam_multi_ex(_p(chunks), chunks.shape[0], total, float(lr), float(beta1), float(beta2), float(eps),
+                               float(weight_decay), float(bc1), float(bc2), 1 if decoupled else 0, _dtype_code(dtype),
+                               _stream_ptr(chunks.device))
     check(rc, "sow_adam_multi")
     launch_counter["kernels"] += 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# live profiling (bench.py)
+# ---------------------------------------------------------------------------------------------------------
+PROF_CLASSES = {"gemm_fwd": 0, "gemm_dx": 1, "gemm_skinny": 2, "gemm_splitk": 3, "merge": 4, "adam": 5}
+
+
+def profile_enable(on: bool) -> None:
+    check(_lib.load().sow_profile_enable(1 if on else 0), "sow_profile_enable")
+
+
+def profile_read(klass: str):
+    """(total_ms, total_work, launches) of one kernel class since profiling was enabled; syncs on its events."""
+    ms, work, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
+    check(_lib.load().sow_profile_read(PROF_CLASSES[klass], ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n)),
+          "sow_profile_read")
+    return ms.value, work.value, n.value

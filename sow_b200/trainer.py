@@ -1,0 +1,139 @@
+"""Synthetic-token SoW pre-training harness: the loop of scripts/simple_train.py:596-650 around the kernel-backed
+``tn_gradient`` API, without the data / W&B / checkpoint plumbing (the driver is the caller
+contract, not part of the hot path).
+
+Loop order is the reference's, including its quirk: at a merge step the gradients were computed w.r.t. the OLD
+factors, then ``accumulate`` + ``reset_optimizer`` run, then the optimizer applies those gradients to the
+re-initialised factors (simple_train.py:618-626 then :646).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .optim import FusedAdamW
+from .parallel import FlatGradSync, broadcast_parameters
+from .surgery import SoWConfig, accumulate, prepare_sow, sow_modules
+
+# shapes of scripts/configs/*.json in the reference (data, not code); vocab 32000, rms_norm_eps 1e-6, silu
+LLAMA_SHAPES: Dict[str, Dict[str, int]] = {
+    "llama_9m": dict(hidden_size=128, intermediate_size=352, num_hidden_layers=4, num_attention_heads=4),
+    "llama_60m": dict(hidden_size=512, intermediate_size=1376, num_hidden_layers=8, num_attention_heads=8),
+    "llama_130m": dict(hidden_size=768, intermediate_size=2048, num_hidden_layers=12, num_attention_heads=12),
+    "llama_350m": dict(hidden_size=1024, intermediate_size=2736, num_hidden_layers=24, num_attention_heads=16),
+    "llama_7b": dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32),
+}
+LLAMA_TARGETS = ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]   # simple_train.py:318
+
+
+def build_llama(name: str, seq_len: int = 256, vocab_size: int = 32000, seed: int = 42) -> nn.Module:
+    """Random-init HF Llama of the named reference config (AutoModelForCausalLM.from_config, simple_train.py:313-314)."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    shp = LLAMA_SHAPES[name]
+    cfg = LlamaConfig(vocab_size=vocab_size, max_position_embeddings=max(1024, seq_len), rms_norm_eps=1e-6,
+                      hidden_act="silu", initializer_range=0.02, bos_token_id=0, eos_token_id=1, use_cache=False,
+                      tie_word_embeddings=False, **shp)
+    torch.manual_seed(seed)
+    return LlamaForCausalLM(cfg)
+
+
+def reset_optimizer(optimizer: torch.optim.Optimizer, group_id: int) -> None:
+    """Zero the Adam state of one param group after a merge, by REBINDING the state tensors -- the contract of
+    scripts/utils/training_utils.py:257-277 that any optimizer used with SoW has to survive."""
+    group = optimizer.param_groups[group_id]
+    for param in group["params"]:
+        state = optimizer.state[param]
+        if not state:
+            continue
+        state["exp_avg"] = torch.zeros_like(param, memory_format=torch.preserve_format)
+        state["exp_avg_sq"] = torch.zeros_like(param, memory_format=torch.preserve_format)
+        if group.get("amsgrad", False):
+            state["max_exp_avg_sq"] = torch.zeros_like(param, memory_format=torch.preserve_format)
+        if "step" in state:
+            state["step"] = torch.zeros_like(state["step"])
+
+
+@dataclass
+class TrainConfig:
+    model: str = "llama_350m"
+    rank: int = 50
+    seq_len: int = 256
+    batch_size: int = 16                 # per GPU
+    lr: float = 1e-2                     # readme.md:5-26
+    sow_lr: float = 1e-3
+    weight_decay: float = 0.0
+    sow_accumulation: int = 5000
+    gradient_accumulation: int = 1
+    grad_clipping: float = 0.0
+    init_method: str = "normal_QR"
+    scale: float = 1.0
+    dtype: torch.dtype = torch.bfloat16
+    seed: int = 42
+    activation_checkpointing: bool = False
+    fused_optimizer: bool = True
+    overlap_grad_sync: bool = True
+
+
+class SoWTrainer:
+    """One process per GPU.  ``step(input_ids)`` = one micro-step of simple_train.py's loop body."""
+
+    def __init__(self, cfg: TrainConfig, device: torch.device):
+        self.cfg = cfg
+        self.device = device
+        model = build_llama(cfg.model, cfg.seq_len, seed=cfg.seed)
+        sow_cfg = SoWConfig(target_modules=LLAMA_TARGETS, rank=cfg.rank, init_method=cfg.init_method, scale=cfg.scale,
+                            decompose=None, device=str(device))
+        model = prepare_sow(model, sow_cfg)                                        # simple_train.py:318-331
+        special, ids = [], set()
+        for m in sow_modules(model):                                                # simple_train.py:389-405
+            for p in list(m.downscale_weights) + list(m.upscale_weights):
+                special.append(p)
+                ids.add(id(p))
+        if cfg.activation_checkpointing:
+            model.gradient_checkpointing_enable()
+        model = model.to(device=device, dtype=cfg.dtype)                           # simple_train.py:425-428
+        self.trainable = [p for p in model.parameters() if p.requires_grad and id(p) not in ids]
+        self.special = special
+        self.model = model
+        groups = [{"params": self.trainable, "lr": cfg.lr, "weight_decay": cfg.weight_decay},
+                  {"params": self.special, "lr": cfg.sow_lr, "weight_decay": cfg.weight_decay}]
+        self.optimizer = FusedAdamW(groups) if cfg.fused_optimizer else torch.optim.AdamW(groups)   # :502-506
+        broadcast_parameters(model)                                                # DDP ctor semantics (:566-572)
+        self.grad_sync = FlatGradSync(self.trainable + self.special, overlap=cfg.overlap_grad_sync)
+        self.global_step = 0
+        self.update_step = 0
+        self.merges = 0
+
+    def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        cfg = self.cfg
+        self.global_step += 1
+        if labels is None:
+            labels = input_ids
+        loss = self.model(input_ids=input_ids, labels=labels).loss                 # simple_train.py:611
+        (loss / cfg.gradient_accumulation).backward()                              # :612-613 (+ overlapped all-reduce)
+        accumulation_step = int(cfg.gradient_accumulation * cfg.sow_accumulation)
+        G = cfg.gradient_accumulation
+        if ((self.global_step % G or G == 1) and self.update_step > 0
+                and self.update_step % accumulation_step == 0):                    # :618-626
+            self.merge()
+        self.grad_sync.synchronize()          # DDP semantics: gradients are averaged on every micro-step (no no_sync)
+        if self.global_step % G != 0:                                              # :628
+            return loss.detach()
+        if cfg.grad_clipping != 0.0:
+            torch.nn.utils.clip_grad_norm_(self.trainable, cfg.grad_clipping)      # :631
+        self.optimizer.step()                                                      # :646
+        self.grad_sync.zero_grad()                                                 # :647 (one memset per bucket)
+        self.update_step += 1
+        return loss.detach()
+
+    def merge(self) -> None:
+        accumulate(self.model)
+        reset_optimizer(self.optimizer, group_id=1)
+        self.merges += 1
+
+    def tokens_per_step(self) -> int:
+        return self.cfg.batch_size * self.cfg.seq_len
