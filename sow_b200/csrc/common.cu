@@ -1,6 +1,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 #include <vector>
@@ -119,8 +120,15 @@ int make_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint6
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapDataType dt = (elem_bytes == 2) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  static const CUtensorMapL2promotion promo = []() {
+    const char* e = getenv("SOWB_TMA_PROMO");   // tuning knob: 0 none, 1 64 B, 2 128 B, 3 256 B (default)
+    const int v = e ? atoi(e) : 3;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                  : (v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                            : (v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+  }();
   CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(SOWB_ECUDA,
                      "cuTensorMapEncodeTiled failed with CUresult %d (base %p inner %llu outer %llu pitch %llu box %ux%u)",

@@ -5,81 +5,216 @@
 //
 // The op is HBM-bound (2 bytes read + 2 bytes written per element) but at r = 50 it needs 25 flop/byte, above what
 // the CUDA cores sustain at full bandwidth, so the rank-r product runs on tcgen05 (one 128x128x64 UMMA block per
-// tile) and everything else is a streaming read-modify-write pipeline:
+// tile) and everything else is a streaming read-modify-write pipeline.  Each matrix is cut into STRIPS of 4 column
+// tiles; the 128x128 tiles of all layers are flattened (layer, strip, m, n-in-strip) and every CTA owns one
+// CONTIGUOUS range of that index space.  The B tiles of a strip stay resident in shared memory while the CTA walks
+// down the strip, and the [128 x r] block of A is staged once per row of the strip, so per tile only W moves
+// (measured: re-fetching the B tile from L2 for every W tile cost 11-16 % of the achieved bandwidth):
 //
-//   warps 4..7 (producer group): thread 0 issues TMA loads of the W_prev tile (2 x [128 rows x 64 cols], swizzle
-//               128B) and of the B tile ([64 k-rows x 128 cols], rows >= r zero-filled by TMA bounds); all 128
-//               threads gather the A tile (pitch r*2 bytes is not TMA-legal) into a zero-padded swizzled smem tile
-//   warp  8   : TMEM allocation; lane 0 issues the UMMA and commits to the accumulator barrier
-//   warps 0..3 (epilogue group): tcgen05.ld accumulator row, add in place onto the W tile in smem (conflict-free
-//               16-byte swizzled accesses), TMA-store the tile back (coalesced, clipped at the matrix edge)
+//   warp  8    : TMA producer.  Per tile: W_prev tile (2 boxes of [128 rows x 64 cols], swizzle 128B) into one of
+//                the W slots.  Per strip: up to 4 B tiles ([64 k-rows x 128 cols], rows >= r zero-filled by the
+//                tensor-map bounds), each issued together with the first W tile that needs it.
+//   warps 10-13: A operand.  Per strip row: ONE bulk copy of the contiguous A[m0:m0+128, 0:r] block (pitch r*2
+//                bytes is not TMA-tensor legal, but the block is contiguous) into a staging buffer, issued one
+//                strip row AHEAD, then repacked (thread per row, conflict-free 4-byte reads when r/2 is odd) into
+//                the zero-padded K-major swizzled operand tile the tensor core reads.
+//   warp  9    : TMEM allocation; lane 0 issues the UMMAs (4 accumulator stages in TMEM = one per W slot, so
+//                the tensor core never waits for the epilogue).
+//   warps 0-7  : epilogue.  tcgen05.ld of the accumulator, add in place onto the W tile in smem (16-byte swizzled
+//                accesses, conflict-free), hand the slot to the store warp.
+//   warps 14-17: store group.  Coalesced 16-byte global stores of the finished tile (2 rows x 256 B per warp
+//                instruction), clipped at the matrix edge; frees the slot.
 //
-// 3 smem slots (W 32 KB + B 16 KB + A 16 KB) keep >= 2 tiles of loads in flight per SM; TMEM double-buffers the
-// accumulator.  Tiles of all layers are flattened into one index space walked persistently by <= #SM CTAs.
+// 4 W slots of 32 KB keep >= 2 tile loads in flight per SM while one tile is in the epilogue and one is being
+// stored.
 #include "common.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 namespace sowb {
 
-constexpr int kMgBM = 128, kMgBN = 128, kMgSlots = 3;
+constexpr int kMgBM = 128, kMgBN = 128, kMgSlots = 3;   // 3 vs 4 slots measured equal: HBM, not latency, binds
 constexpr int kMgWBytes = kMgBM * kMgBN * 2;        // 32 KB
 constexpr int kMgBBytes = 64 * kMgBN * 2;           // 16 KB
-constexpr int kMgABytes = kMgBM * 64 * 2;           // 16 KB
-constexpr int kMgSlotBytes = kMgWBytes + kMgBBytes + kMgABytes;
-constexpr int kMgMaxEntries = 2048;   // per launch (host splits longer tables)
-constexpr int kMgSmemTotal = 1024 + kMgSlots * kMgSlotBytes + 256 + kMgMaxEntries * 4;
-constexpr int kMgThreads = 288;
-constexpr uint32_t kMgTmemCols = 256;
+constexpr int kMgABytes = kMgBM * 64 * 2;           // 16 KB (operand tile and staging buffer)
+constexpr int kMgSlotBytes = kMgWBytes;
+constexpr int kMgStrip = 4;                         // column tiles per strip (B tiles resident in smem)
+constexpr int kMgAcc = 4;                           // TMEM accumulator stages
+constexpr int kMgMaxEntries = 384;                  // per launch (longer tables are split by the host)
+constexpr int kMgNumBars = 3 * kMgSlots + 2 * kMgAcc + 4 + 2 * kMgStrip;   // + one 8-byte cell for the TMEM address
+constexpr int kMgBarBytes = 320;
+static_assert((kMgNumBars + 1) * 8 <= kMgBarBytes, "barrier block overflows into the entry table");
+constexpr int kMgSmemTotal =
+    1024 + kMgSlots * kMgSlotBytes + kMgStrip * kMgBBytes + 2 * kMgABytes + kMgBarBytes + kMgMaxEntries * 56;
+constexpr int kMgThreads = 576;
+constexpr int kMgStoreThreads = 128;
+constexpr int kMgEpiThreads = 256;
+constexpr int kMgRepackThreads = 128;
+constexpr uint32_t kMgTmemCols = kMgAcc * kMgBN;   // 512: the whole TMEM (1 CTA per SM)
+static_assert(kMgSmemTotal <= 232448, "merge kernel exceeds the 227 KB shared-memory opt-in limit");
 
 struct alignas(128) MergeDevEntry {
   CUtensorMap tmWin;   // W_prev loads  (box 64 cols x 128 rows)
   CUtensorMap tmWout;  // W stores
   CUtensorMap tmB;     // B[r, out] as MN-major operand (box 64 cols x 64 rows)
   const __nv_bfloat16* A;
+  __nv_bfloat16* W;    // destination matrix
   int lda;             // row pitch of A in elements (= full rank)
   int in, out, r;      // r = rank chunk handled by this entry (<= 64)
   float scale;
   int m_tiles, n_tiles, tile_begin;
   int has_prev;
+  int a_bulk;          // the [rows x r] blocks of A are contiguous, 16-byte aligned and a multiple of 16 bytes long
 };
 
-// Tiles are visited in increasing order by every role, so the entry index only ever moves forward: walk it.
-// `ends` (smem) holds tile_begin + #tiles of every entry, staged once per CTA.
-__device__ __forceinline__ int advance_entry(const int* __restrict__ ends, int ei, int tile) {
-  while (tile >= ends[ei]) ++ei;
-  return ei;
-}
+// Scalar part of an entry, staged in shared memory at kernel start: under HBM saturation a global load costs
+// microseconds, and every role needs these fields whenever its range crosses into the next matrix.
+struct MergeInfo {
+  const __nv_bfloat16* A;
+  __nv_bfloat16* W;
+  int lda, in, out, r;
+  float scale;
+  int m_tiles, n_tiles, tile_end;
+  int has_prev, a_bulk;
+};
+static_assert(sizeof(MergeInfo) == 56, "MergeInfo layout");
+
+// Position of one CTA inside the flattened (entry, strip, m-tile, n-in-strip) space.  Every role walks the same
+// sequence of tiles.
+struct MergeCursor {
+  const MergeDevEntry* tab;   // global: tensor maps
+  const MergeInfo* info;      // smem: scalar fields of every entry
+  int ei, ebeg, nt, mtiles;
+  int prev_mt, prev_strip;
+  bool entry_changed, new_strip, new_item, last_of_item, b_first_use, b_last_use;
+  int m0, n0, mt, strip, j, width;
+  const MergeInfo* e;
+  const MergeDevEntry* g;
+  int n_entries;
+
+  __device__ __forceinline__ void init(const MergeDevEntry* t, const MergeInfo* inf, int n, int first_tile) {
+    tab = t;
+    info = inf;
+    n_entries = n;
+    int lo = 0, hi = n_entries - 1;   // smallest ei with tile_end > first_tile
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (info[mid].tile_end > first_tile) hi = mid; else lo = mid + 1;
+    }
+    ei = lo;
+    ebeg = ei ? info[ei - 1].tile_end : 0;
+    e = &info[ei];
+    g = &tab[ei];
+    nt = e->n_tiles;
+    mtiles = e->m_tiles;
+    prev_mt = -1;
+    prev_strip = -1;
+    entry_changed = true;
+  }
+  // [first, last] = this CTA's range of tiles
+  __device__ __forceinline__ void seek(int tile, int first, int last) {
+    bool changed = entry_changed && prev_mt < 0;   // first tile of this CTA
+    while (tile >= info[ei].tile_end) {
+      ebeg = info[ei].tile_end;
+      ++ei;
+      changed = true;
+    }
+    if (changed) {
+      e = &info[ei];
+      g = &tab[ei];
+      nt = e->n_tiles;
+      mtiles = e->m_tiles;
+    }
+    entry_changed = changed;
+    const int local = tile - ebeg;
+    const int per_full = mtiles * kMgStrip;          // tiles in a full strip
+    strip = local / per_full;
+    const int rem = local - strip * per_full;
+    width = min(kMgStrip, nt - strip * kMgStrip);     // only the last strip of a matrix can be narrower
+    mt = rem / width;
+    j = rem - mt * width;
+    new_strip = changed || strip != prev_strip;
+    new_item = new_strip || mt != prev_mt;
+    prev_mt = mt;
+    prev_strip = strip;
+    last_of_item = (j == width - 1) || tile == last;
+    // B tile j of a strip is used by tiles (tile0 + j + k*width): first / last use inside this CTA's range
+    b_first_use = mt == 0 || tile - width < first;
+    b_last_use = mt == mtiles - 1 || tile + width > last;
+    m0 = mt * kMgBM;
+    n0 = (strip * kMgStrip + j) * kMgBN;
+  }
+};
 
 __global__ void __launch_bounds__(kMgThreads, 1)
-sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total_tiles) {
+sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total_tiles, long long* __restrict__ dbg_ts) {
+  // debug timeline (SOWB_MERGE_TS): CTA 0 records clock64 stamps per tile: [tile][8]
+  auto stamp = [&](int tile_local, int k) {
+    if (dbg_ts != nullptr && blockIdx.x == 0 && tile_local < 256) dbg_ts[tile_local * 8 + k] = clock64();
+  };
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMgSlots * kMgSlotBytes);
-  uint64_t* full_bar = bars;                    // [slots] 128 A-writers + 1 expect_tx
-  uint64_t* empty_bar = bars + kMgSlots;        // [slots] 1
-  uint64_t* tfull_bar = bars + 2 * kMgSlots;    // [2]
-  uint64_t* tempty_bar = bars + 2 * kMgSlots + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMgSlots + 4);
-  int* ends = reinterpret_cast<int*>(smem + kMgSlots * kMgSlotBytes + 256);
+  uint8_t* sBt = smem + kMgSlots * kMgSlotBytes;      // the strip's B tiles (MN-major swizzled operands)
+  uint8_t* sA = sBt + kMgStrip * kMgBBytes;           // K-major swizzled A operand tile
+  uint8_t* stage = sA + kMgABytes;                    // raw [rows x r] block of A
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + kMgABytes);
+  uint64_t* full_bar = bars;                          // [slots] 1 + tx      : W_prev landed
+  uint64_t* empty_bar = bars + kMgSlots;              // [slots] 1           : store has read the slot
+  uint64_t* wready_bar = bars + 2 * kMgSlots;         // [slots] 256         : epilogue finished the tile
+  uint64_t* tfull_bar = bars + 3 * kMgSlots;          // [kMgAcc] 1 (umma commit)
+  uint64_t* tempty_bar = tfull_bar + kMgAcc;          // [kMgAcc] 256
+  uint64_t* astage_full = tempty_bar + kMgAcc;        // 1 + tx
+  uint64_t* astage_empty = astage_full + 1;           // 128
+  uint64_t* a_full = astage_full + 2;                 // 128
+  uint64_t* a_empty = astage_full + 3;                // 1 (umma commit)
+  uint64_t* b_full = astage_full + 4;                 // [kMgStrip] 1 + tx
+  uint64_t* b_empty = b_full + kMgStrip;              // [kMgStrip] 1 (umma commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMgStrip);
+  MergeInfo* info = reinterpret_cast<MergeInfo*>(reinterpret_cast<uint8_t*>(bars) + kMgBarBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < n_entries; i += kMgThreads) ends[i] = tab[i].tile_begin + tab[i].m_tiles * tab[i].n_tiles;
+  for (int i = threadIdx.x; i < n_entries; i += kMgThreads) {
+    const MergeDevEntry* t = &tab[i];
+    MergeInfo mi;
+    mi.A = t->A;
+    mi.W = t->W;
+    mi.lda = t->lda;
+    mi.in = t->in;
+    mi.out = t->out;
+    mi.r = t->r;
+    mi.scale = t->scale;
+    mi.m_tiles = t->m_tiles;
+    mi.n_tiles = t->n_tiles;
+    mi.tile_end = t->tile_begin + t->m_tiles * t->n_tiles;
+    mi.has_prev = t->has_prev;
+    mi.a_bulk = t->a_bulk;
+    info[i] = mi;
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMgSlots; ++i) {
-      mbar_init(&full_bar[i], 129);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kMgStoreThreads);
+      mbar_init(&wready_bar[i], kMgEpiThreads);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMgAcc; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kMgEpiThreads);
     }
+    for (int i = 0; i < kMgStrip; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(astage_full, 1);
+    mbar_init(astage_empty, kMgRepackThreads);
+    mbar_init(a_full, kMgRepackThreads);
+    mbar_init(a_empty, 1);
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, kMgTmemCols);
     tmem_relinquish();
   }
@@ -88,173 +223,268 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
-    // ===================== producer group =====================
-    const int pt = threadIdx.x - 128;  // 0..127
-    const MergeDevEntry* last_e = nullptr;
-    int slot = 0, ei = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      ei = advance_entry(ends, ei, tile);
-      const MergeDevEntry* e = &tab[ei];
-      const int local = tile - e->tile_begin;
-      const int m0 = (local / e->n_tiles) * kMgBM;
-      const int n0 = (local % e->n_tiles) * kMgBN;
-      uint8_t* sW = smem + slot * kMgSlotBytes;
-      uint8_t* sB = sW + kMgWBytes;
-      uint8_t* sA = sB + kMgBBytes;
-      // issue the A loads BEFORE waiting for the slot: their latency overlaps the wait
-      const __nv_bfloat16* A = e->A;
-      const int r = e->r, lda = e->lda, rows = min(kMgBM, e->in - m0);
-      const bool vec = (lda == r) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((r & 7) == 0 || (m0 * r) % 8 == 0);
-      uint4 av[8];
-      const int nvec = (rows * r) >> 3;                 // whole 8-element groups of the contiguous [rows x r] block
-      if (vec) {
-        const uint4* src = reinterpret_cast<const uint4*>(A + static_cast<int64_t>(m0) * r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int v = pt + 128 * j;
-          if (v < nvec) av[j] = __ldg(src + v);
+  const int lo = static_cast<int>(static_cast<int64_t>(blockIdx.x) * total_tiles / gridDim.x);
+  const int hi = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * total_tiles / gridDim.x);
+
+  if (warp == 8) {
+    if (lane == 0 && lo < hi) {
+      // ===================== TMA producer =====================
+      MergeCursor c;
+      c.init(tab, info, n_entries, lo);
+      int slot = 0;
+      uint32_t phase = 0, b_phases = 0;   // b_phases: one parity bit per resident B tile
+      const uint64_t pol_keep = l2_policy_evict_last();
+      for (int tile = lo; tile < hi; ++tile) {
+        c.seek(tile, lo, hi - 1);
+        const MergeInfo* e = c.e;
+        if (c.entry_changed) {
+          // descriptors live in global memory: fetch the NEXT matrix's into the descriptor cache now, so that the
+          // first loads of that matrix do not wait a (loaded) HBM round trip
+          if (tile == lo) {
+            tma_acquire_desc(&c.g->tmWin);
+            tma_acquire_desc(&c.g->tmB);
+          }
+          if (c.ei + 1 < n_entries) {
+            tma_acquire_desc(&c.g[1].tmWin);
+            tma_acquire_desc(&c.g[1].tmB);
+            tma_prefetch_desc(&c.g[1].tmWin);
+            tma_prefetch_desc(&c.g[1].tmB);
+          }
         }
-      }
-      mbar_wait(&empty_bar[slot], phase ^ 1);
-      if (pt == 0) {
-        if (e != last_e) {
-          tma_acquire_desc(&e->tmWin);
-          tma_acquire_desc(&e->tmB);
-          last_e = e;
-        }
-        mbar_expect_tx(&full_bar[slot], kMgBBytes + (e->has_prev ? kMgWBytes : 0));
+        // W first: it depends on nothing but a free slot
+        uint8_t* sW = smem + slot * kMgSlotBytes;
+        stamp(tile - lo, 0);
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        stamp(tile - lo, 1);
         if (e->has_prev) {
-          tma_load_2d(sW, &e->tmWin, &full_bar[slot], n0, m0);
-          tma_load_2d(sW + 16384, &e->tmWin, &full_bar[slot], n0 + 64, m0);
+          mbar_expect_tx(&full_bar[slot], kMgWBytes);
+          // default L2 policy on purpose: the line must still be in L2 when the store group writes it back a few
+          // microseconds later (measured: evict_first loads / streaming stores cost 8 % of the achieved bandwidth)
+          tma_load_2d(sW, &c.g->tmWin, &full_bar[slot], c.n0, c.m0);
+          tma_load_2d(sW + 16384, &c.g->tmWin, &full_bar[slot], c.n0 + 64, c.m0);
+        } else {
+          mbar_arrive(&full_bar[slot]);
         }
-        tma_load_2d(sB, &e->tmB, &full_bar[slot], n0, 0);
-        tma_load_2d(sB + 8192, &e->tmB, &full_bar[slot], n0 + 64, 0);
+        if (++slot == kMgSlots) {
+          slot = 0;
+          phase ^= 1;
+        }
+        if (c.b_first_use) {
+          // B tile j of this strip travels with the first W tile that needs it; its buffer is free once the last
+          // UMMA of the previous strip that read it has completed (issued >= 4 tiles ago)
+          uint8_t* sB = sBt + c.j * kMgBBytes;
+          mbar_wait(&b_empty[c.j], ((b_phases >> c.j) & 1u) ^ 1u);
+          mbar_expect_tx(&b_full[c.j], kMgBBytes);
+          tma_load_2d_hint(sB, &c.g->tmB, &b_full[c.j], c.n0, 0, pol_keep);
+          tma_load_2d_hint(sB + 8192, &c.g->tmB, &b_full[c.j], c.n0 + 64, 0, pol_keep);
+          b_phases ^= 1u << c.j;
+        }
       }
-      // A[m0 : m0+128, 0 : r] -> K-major swizzled tile, zero padded to 64 columns
-      auto put = [&](int row, int col, __nv_bfloat16 v) {
-        *reinterpret_cast<__nv_bfloat16*>(sA + row * 128 + (((col >> 3) ^ (row & 7)) << 4) + (col & 7) * 2) = v;
-      };
-      if (vec) {
-        // 1) zero the padding columns r..63 (and rows beyond the matrix edge), 16 B at a time where possible
-        for (int idx = pt; idx < kMgBM * 8; idx += 128) {
-          const int row = idx >> 3, chunk = idx & 7;
-          if (row >= rows || chunk * 8 >= r)
-            *reinterpret_cast<uint4*>(sA + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-          else if (chunk * 8 + 8 > r)
-            for (int c = r; c < chunk * 8 + 8; ++c) put(row, c, __float2bfloat16(0.f));
+    }
+  } else if (warp >= 10 && warp < 14) {
+    // ===================== A repack group =====================
+    if (lo < hi) {
+      const int row = threadIdx.x - 320;  // 0..127: one row of the operand tile per thread
+      MergeCursor c, nx;                  // nx runs one strip row ahead: its A block is fetched while c's is used
+      c.init(tab, info, n_entries, lo);
+      nx.init(tab, info, n_entries, lo);
+      int nx_tile = lo;
+      const uint64_t pol_keep = l2_policy_evict_last();
+      auto prefetch_next_item = [&]() {
+        while (nx_tile < hi) {
+          nx.seek(nx_tile, lo, hi - 1);
+          ++nx_tile;
+          if (nx.new_item) {
+            if (nx.e->a_bulk && row == 0) {
+              const int rows = min(kMgBM, nx.e->in - nx.m0);
+              const uint32_t bytes = static_cast<uint32_t>(rows) * nx.e->r * 2u;
+              mbar_expect_tx(astage_full, bytes);
+              bulk_load_1d_hint(stage, nx.e->A + static_cast<int64_t>(nx.m0) * nx.e->r, bytes, astage_full, pol_keep);
+            }
+            return;
+          }
         }
-        // 2) scatter the prefetched 16-byte groups (a group may straddle two rows when r % 8 != 0)
+      };
+      prefetch_next_item();
+      uint32_t st_phase = 0, ae_phase = 0;
+      for (int tile = lo; tile < hi; ++tile) {
+        c.seek(tile, lo, hi - 1);
+        if (!c.new_item) continue;
+        const MergeInfo* e = c.e;
+        const int r = e->r, lda = e->lda;
+        const bool live = row < min(kMgBM, e->in - c.m0);
+        uint32_t w[32];  // the row as 32 packed bf16 pairs, zero beyond r
+        if (e->a_bulk) {
+          mbar_wait(astage_full, st_phase);
+          st_phase ^= 1;
+          if ((r & 1) == 0) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(stage + row * r * 2);
+            const int words = r >> 1;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int v = pt + 128 * j;
-          if (v < nvec) {
-            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&av[j]);
-            int e0 = v * 8;
-            int row = e0 / r, col = e0 - row * r;
+            for (int j = 0; j < 32; ++j) w[j] = (live && j < words) ? src[j] : 0u;
+          } else {
+            const uint16_t* src = reinterpret_cast<const uint16_t*>(stage) + row * r;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              put(row, col, h[q]);
-              if (++col == r) {
-                col = 0;
-                ++row;
-              }
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t lo16 = (live && 2 * j < r) ? src[2 * j] : 0u;
+              const uint32_t hi16 = (live && 2 * j + 1 < r) ? src[2 * j + 1] : 0u;
+              w[j] = lo16 | (hi16 << 16);
+            }
+          }
+        } else {
+          const uint16_t* src = reinterpret_cast<const uint16_t*>(e->A) + static_cast<int64_t>(c.m0 + row) * lda;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t lo16 = (live && 2 * j < r) ? __ldg(src + 2 * j) : 0u;
+            const uint32_t hi16 = (live && 2 * j + 1 < r) ? __ldg(src + 2 * j + 1) : 0u;
+            w[j] = lo16 | (hi16 << 16);
+          }
+        }
+        // every thread has its row in registers: the staging buffer can take the next strip row's block now
+        named_barrier_sync(2, kMgRepackThreads);
+        prefetch_next_item();
+        mbar_wait(a_empty, ae_phase ^ 1);   // the UMMAs of the previous row of tiles have read sA
+        ae_phase ^= 1;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(sA + row * 128 + ((ch ^ (row & 7)) << 4)) =
+              make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(a_full);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0 && lo < hi) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc(1, kMgBM, kMgBN, 0, 1);
+      MergeCursor c;
+      c.init(tab, info, n_entries, lo);
+      int acc = 0;
+      uint32_t acc_phase = 0, af_phase = 0, b_phases = 0;
+      const uint32_t sAu = smem_u32(sA), sBu = smem_u32(sBt);
+      for (int tile = lo; tile < hi; ++tile) {
+        c.seek(tile, lo, hi - 1);
+        const int ksteps = (c.e->r + 15) >> 4;
+        if (c.b_first_use) {
+          mbar_wait(&b_full[c.j], (b_phases >> c.j) & 1u);
+          b_phases ^= 1u << c.j;
+        }
+        if (c.new_item) {
+          mbar_wait(a_full, af_phase);
+          af_phase ^= 1;
+        }
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t sB = sBu + c.j * kMgBBytes;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_smem_desc(sAu + k * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(sB + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base + acc * kMgBN, ad, bd, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&tfull_bar[acc]);
+        // sA / the B tiles may be overwritten once the UMMAs issued so far are done
+        if (c.last_of_item) umma_commit(a_empty);
+        if (c.b_last_use) umma_commit(&b_empty[c.j]);
+        if (++acc == kMgAcc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 14) {
+    // ===================== store group =====================
+    // Plain coalesced 16-byte stores (each warp instruction writes 2 rows x 256 contiguous bytes); measured 1-2 %
+    // faster than a TMA store of the same tile, and it takes the write-back off the TMA unit that feeds the loads.
+    if (lo < hi) {
+      const int st = threadIdx.x - 448;          // 0..127
+      const int sw = st >> 5;
+      const int sub = lane >> 4;                 // which of the 2 rows of this warp instruction
+      const int chunk16 = lane & 15;             // 16-byte chunk inside the 256-byte tile row
+      const int half = chunk16 >> 3, ch = chunk16 & 7;
+      MergeCursor c;
+      c.init(tab, info, n_entries, lo);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = lo; tile < hi; ++tile) {
+        c.seek(tile, lo, hi - 1);
+        const MergeInfo* e = c.e;
+        const uint8_t* sW = smem + slot * kMgSlotBytes + half * 16384;
+        const int col = c.n0 + chunk16 * 8;
+        const bool col_ok = col < e->out;        // out % 8 == 0: a 16-byte chunk never straddles the edge
+        const int rows = min(kMgBM, e->in - c.m0);
+        __nv_bfloat16* gbase = e->W + static_cast<int64_t>(c.m0) * e->out + col;
+        mbar_wait(&wready_bar[slot], phase);
+        if (st == 0) stamp(tile - lo, 6);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          uint4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = ((b * 8 + i) * 4 + sw) * 2 + sub;
+            v[i] = *reinterpret_cast<const uint4*>(sW + row * 128 + ((ch ^ (row & 7)) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = ((b * 8 + i) * 4 + sw) * 2 + sub;
+            if (col_ok && row < rows) {
+              uint4* dst = reinterpret_cast<uint4*>(gbase + static_cast<int64_t>(row) * e->out);
+              *dst = v[i];
             }
           }
         }
-        for (int e1 = nvec * 8 + pt; e1 < rows * r; e1 += 128) {   // tail elements of the block
-          const int row = e1 / r, col = e1 - row * r;
-          put(row, col, A[static_cast<int64_t>(m0) * r + e1]);
-        }
-      } else {
-        const int col = pt & 63;
-#pragma unroll 8
-        for (int j = 0; j < 64; ++j) {
-          const int row = (pt >> 6) + 2 * j;
-          __nv_bfloat16 v = __float2bfloat16(0.f);
-          if (col < r && row < rows) v = A[static_cast<int64_t>(m0 + row) * lda + col];
-          put(row, col, v);
+        if (st == 0) stamp(tile - lo, 7);
+        mbar_arrive(&empty_bar[slot]);           // this thread's part of the slot is in registers / on its way
+        if (++slot == kMgSlots) {
+          slot = 0;
+          phase ^= 1;
         }
       }
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&full_bar[slot]);
-      if (++slot == kMgSlots) {
-        slot = 0;
-        phase ^= 1;
-      }
     }
-  } else if (warp == 8 && lane == 0) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(1, kMgBM, kMgBN, 0, 1);
-    int slot = 0, acc = 0, ei = 0;
-    uint32_t phase = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      ei = advance_entry(ends, ei, tile);
-      const MergeDevEntry* e = &tab[ei];
-      const int ksteps = (e->r + 15) >> 4;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      mbar_wait(&full_bar[slot], phase);
-      tc_fence_after();
-      const uint32_t sW = smem_u32(smem + slot * kMgSlotBytes);
-      const uint32_t sB = sW + kMgWBytes, sA = sB + kMgBBytes;
-      for (int k = 0; k < ksteps; ++k) {
-        const uint64_t ad = make_smem_desc(sA + k * 32, 16, 1024);
-        const uint64_t bd = make_smem_desc(sB + k * 2048, 8192, 1024);
-        umma_bf16(tmem_base + acc * kMgBN, ad, bd, idesc, k > 0 ? 1u : 0u);
-      }
-      umma_commit(&tfull_bar[acc]);
-      if (++slot == kMgSlots) {
-        slot = 0;
-        phase ^= 1;
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-  } else if (warp < 4) {
+  } else if (warp < 8) {
     // ===================== epilogue group =====================
-    const int et = threadIdx.x;
-    const int row = warp * 32 + lane;
-    int slot = 0, acc = 0, ei = 0;
-    uint32_t phase = 0, acc_phase = 0;
-    int prev_slot = -1;
-    const MergeDevEntry* last_e = nullptr;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      ei = advance_entry(ends, ei, tile);
-      const MergeDevEntry* e = &tab[ei];
-      const int local = tile - e->tile_begin;
-      const int m0 = (local / e->n_tiles) * kMgBM;
-      const int n0 = (local % e->n_tiles) * kMgBN;
-      const float scale = e->scale;
-      const bool has_prev = e->has_prev != 0;
-      uint8_t* sW = smem + slot * kMgSlotBytes;
-      mbar_wait(&full_bar[slot], phase);  // W tile landed (acquire on the TMA barrier)
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * kMgBN;
-#pragma unroll
-      for (int q = 0; q < kMgBN / 32; ++q) {
-        uint32_t v[32];
-        tmem_ld32(taddr + q * 32, v);
+    if (lo < hi) {
+      const int q = warp & 3;            // TMEM lane quarter this warp may read
+      const int half = warp >> 2;        // 64-column half of the tile (= one TMA box of the W slot)
+      const int row = q * 32 + lane;
+      MergeCursor c;
+      c.init(tab, info, n_entries, lo);
+      int slot = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      float scale = 0.f;
+      bool has_prev = false;
+      for (int tile = lo; tile < hi; ++tile) {
+        c.seek(tile, lo, hi - 1);
+        if (c.entry_changed) {
+          scale = c.e->scale;
+          has_prev = c.e->has_prev != 0;
+        }
+        uint8_t* box = smem + slot * kMgSlotBytes + half * 16384 + row * 128;
+        if (threadIdx.x == 0) stamp(tile - lo, 2);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        if (threadIdx.x == 0) stamp(tile - lo, 3);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kMgBN + half * 64;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32, v1);
+        mbar_wait(&full_bar[slot], phase);  // W tile landed (acquire on the TMA barrier)
+        if (threadIdx.x == 0) stamp(tile - lo, 4);
         tmem_ld_wait();
-        uint8_t* box = sW + (q >> 1) * 16384 + row * 128;
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);      // accumulator is in registers: hand the TMEM stage back
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int chunk = (q & 1) * 4 + c;
-          uint4* p = reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4));
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4* p = reinterpret_cast<uint4*>(box + ((ch ^ (row & 7)) << 4));
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = scale * __uint_as_float(v[c * 8 + j]);
+          for (int j = 0; j < 8; ++j) f[j] = scale * __uint_as_float(ch < 4 ? v0[ch * 8 + j] : v1[(ch - 4) * 8 + j]);
           if (has_prev) {
             const uint4 old = *p;
-            const uint32_t w[4] = {old.x, old.y, old.z, old.w};
+            const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-              f[2 * j] += __low2float(b);
-              f[2 * j + 1] += __high2float(b);
+              f[2 * j] += __uint_as_float(ow[j] << 16);
+              f[2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u);
             }
           }
           uint4 pk;
@@ -264,47 +494,40 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
           pk.w = pack_bf16x2(f[6], f[7]);
           *p = pk;
         }
-      }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-      fence_proxy_async_smem();
-      named_barrier_sync(1, 128);
-      if (et == 0) {
-        if (e != last_e) {
-          tma_acquire_desc(&e->tmWout);
-          last_e = e;
+        fence_proxy_async_smem();
+        mbar_arrive(&wready_bar[slot]);
+        if (threadIdx.x == 0) stamp(tile - lo, 5);
+        if (++slot == kMgSlots) {
+          slot = 0;
+          phase ^= 1;
         }
-        tma_store_2d(&e->tmWout, sW, n0, m0);
-        if (n0 + 64 < e->out) tma_store_2d(&e->tmWout, sW + 16384, n0 + 64, m0);
-        tma_store_commit();
-        if (prev_slot >= 0) {
-          tma_store_wait_read<1>();  // the previous tile's store has finished reading its slot
-          mbar_arrive(&empty_bar[prev_slot]);
+        if (++acc == kMgAcc) {
+          acc = 0;
+          acc_phase ^= 1;
         }
-      }
-      prev_slot = slot;
-      if (++slot == kMgSlots) {
-        slot = 0;
-        phase ^= 1;
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
-    if (et == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem_base, kMgTmemCols);
+  if (warp == 9) tmem_dealloc(tmem_base, kMgTmemCols);
 }
 
 }  // namespace sowb
 
 using namespace sowb;
 
+static long long* g_merge_ts = nullptr;   // debug timeline buffer (device), see sow_merge_debug_timeline
+
 extern "C" {
+
+// Debug aid (not part of the product ABI): device buffer of 256*8 int64 that CTA 0 of the next merge launches
+// fills with clock64 stamps per tile; pass NULL to switch off.
+int sow_merge_debug_timeline(void* buf) {
+  g_merge_ts = static_cast<long long*>(buf);
+  return SOWB_OK;
+}
 
 size_t sow_merge_table_stride(void) {
   // one device entry per 64-wide rank chunk; callers size the table for ceil(r/64) chunks per layer
@@ -332,11 +555,11 @@ int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* t
     return set_error(SOWB_EWORKSPACE, "sow_merge_grouped: table %zu B < required %zu B", table_bytes,
                      size_t(n) * sizeof(MergeDevEntry));
   SOWB_CHECK_CUDA(cudaFuncSetAttribute(sow_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmemTotal));
+  const int sms = num_sms();
   // ranks above 64 are applied as successive 64-wide chunks (W_prev = W after the first chunk)
   for (int chunk = 0; chunk < max_chunks; ++chunk) {
     std::vector<MergeDevEntry> host;
     host.reserve(n);
-    int tiles = 0;
     for (int i = 0; i < n; ++i) {
       const sowb_merge_entry& e = entries[i];
       const int r0 = chunk * 64;
@@ -357,6 +580,7 @@ int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* t
       rc = make_tensor_map_2d(&d.tmB, Bp, e.out, rc_rows, uint64_t(e.out) * 2, 64, 64, 2);
       if (rc) return rc;
       d.A = static_cast<const __nv_bfloat16*>(e.A) + r0;
+      d.W = static_cast<__nv_bfloat16*>(e.W);
       d.lda = e.r;
       d.in = e.in;
       d.out = e.out;
@@ -364,23 +588,32 @@ int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* t
       d.scale = e.scale;
       d.m_tiles = ceil_div(e.in, kMgBM);
       d.n_tiles = ceil_div(e.out, kMgBN);
-      d.tile_begin = tiles;
-      tiles += d.m_tiles * d.n_tiles;
+      // bulk-copy staging of A needs contiguous, 16-byte aligned blocks whose length is a multiple of 16 bytes
+      d.a_bulk = (e.r <= 64) && ((reinterpret_cast<uintptr_t>(e.A) & 15) == 0) &&
+                 (((e.in % kMgBM) * e.r) % 8 == 0);
       host.push_back(d);
     }
     if (host.empty()) break;
-    if (host.size() > size_t(kMgMaxEntries))
-      return set_error(SOWB_EINVAL, "sow_merge_grouped: at most %d entries per call", kMgMaxEntries);
-    SOWB_CHECK_CUDA(cudaMemcpyAsync(table_dev, host.data(), host.size() * sizeof(MergeDevEntry),
-                                    cudaMemcpyHostToDevice, stream));
-    const int sms = num_sms();
-    const int grid = tiles < sms ? tiles : sms;
-    double bytes = 0;   // algorithmic: W read (if any) + W write + A + B
-    for (const auto& d : host) bytes += 2.0 * d.in * d.out * (1 + d.has_prev) + 2.0 * d.r * (double(d.in) + d.out);
-    ProfileScope prof(stream, PROF_MERGE, bytes);
-    sow_merge_kernel<<<grid, kMgThreads, kMgSmemTotal, stream>>>(static_cast<const MergeDevEntry*>(table_dev),
-                                                                 static_cast<int>(host.size()), tiles);
-    SOWB_CHECK_CUDA(cudaGetLastError());
+    // the device table holds at most kMgMaxEntries entries per launch
+    for (size_t first = 0; first < host.size(); first += kMgMaxEntries) {
+      const size_t cnt = std::min(host.size() - first, size_t(kMgMaxEntries));
+      int tiles = 0;
+      double bytes = 0;   // algorithmic: W read (if any) + W write + A + B
+      for (size_t j = first; j < first + cnt; ++j) {
+        MergeDevEntry& d = host[j];
+        d.tile_begin = tiles;
+        tiles += d.m_tiles * d.n_tiles;
+        bytes += 2.0 * d.in * d.out * (1 + d.has_prev) + 2.0 * d.r * (double(d.in) + d.out);
+      }
+      // stream-ordered: an earlier launch on this stream that still reads the table finishes before this copy
+      SOWB_CHECK_CUDA(cudaMemcpyAsync(table_dev, host.data() + first, cnt * sizeof(MergeDevEntry),
+                                      cudaMemcpyHostToDevice, stream));
+      const int grid = tiles < sms ? tiles : sms;
+      ProfileScope prof(stream, PROF_MERGE, bytes);
+      sow_merge_kernel<<<grid, kMgThreads, kMgSmemTotal, stream>>>(static_cast<const MergeDevEntry*>(table_dev),
+                                                                   static_cast<int>(cnt), tiles, g_merge_ts);
+      SOWB_CHECK_CUDA(cudaGetLastError());
+    }
   }
   return SOWB_OK;
 }

@@ -57,7 +57,8 @@ def test_merge_matches_reference_golden(golden_merge, case):
 
 @pytest.mark.parametrize("fin,fout,r,scale,has_prev", [
     (1024, 1024, 50, 1.0, True), (1024, 2736, 50, 1.0, True), (2736, 1024, 50, 0.5, False),
-    (768, 3072, 8, 0.125, True), (4096, 11008, 8, 0.125, True), (264, 136, 50, 1.0, True), (128, 128, 200, 1.0, True)])
+    (768, 3072, 8, 0.125, True), (4096, 11008, 8, 0.125, True), (264, 136, 50, 1.0, True), (128, 128, 200, 1.0, True),
+    (100, 136, 7, 1.0, True), (204, 128, 33, 0.5, False), (1000, 264, 64, 1.0, True), (384, 2736, 16, 2.0, True)])
 def test_merge_vs_oracle_at_baseline_shapes(fin, fout, r, scale, has_prev):
     rng = np.random.default_rng(7)
     A = O.bf16_round(rng.standard_normal((fin, r), dtype=np.float32) * 0.05)
