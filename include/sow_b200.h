@@ -152,6 +152,23 @@ int tt_adam_fused2(void* p, const void* g, const float* G1m, const float* G2m, c
                    double beta1, double beta2, double eps, double step_size, double lr_wd, int first_step,
                    int dtype, void* stream);
 
+/*
+ * Order-2 TT-Adam with the re-compression fused in: the dense moments never reach HBM.  Same math as tt_adam_fused2
+ * followed by sow_thin_qr + tt_project on its outputs, in three steps (ttadam.py:61-115):
+ *   1. tt_adam2_head  : X{m,v}[P, 64] = the first 64 columns of the NEW moments (interleaved layout, P = mm*nn).
+ *                       p is not modified.
+ *   2. sow_thin_qr    : Q'{m,v}[P, r] from the first r columns of X{m,v}      (caller, batch = 2, ldx = 64)
+ *   3. tt_adam2_fused : Adam update of p  +  R'{m,v}[r, P] += Q'^T . (new moments), accumulated tile by tile in
+ *                       registers; R' must be zero-filled by the caller (fp32 red.add across row ranges).
+ * New cores: G1' = Q' (P x r), G2' = R' (r x P).  r <= 64.  first_step != 0 -> previous moments are zero.
+ */
+int tt_adam2_head(const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r, float* Xm,
+                  float* Xv, int M, int N, int mm, int nn, double beta1, double beta2, int first_step, int dtype,
+                  void* stream);
+int tt_adam2_fused(void* p, const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r,
+                   const float* Qm, const float* Qv, float* Rm, float* Rv, int M, int N, int mm, int nn, double beta1,
+                   double beta2, double eps, double step_size, double lr_wd, int first_step, int dtype, void* stream);
+
 /* Same update on dense fp32 moments m, v of shape (M,N) (order > 2 path); v is clamped at 0 first (ttadam.py:84). */
 int tt_adam_dense(void* p, const void* g, float* m, float* v, int64_t numel, double beta1, double beta2, double eps,
                   double step_size, double lr_wd, int dtype, void* stream);

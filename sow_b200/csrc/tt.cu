@@ -143,6 +143,154 @@ thin_qr_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cholesky-QR for r <= 64 (the TT ranks 8-64 and the SoW rank 50): three fully parallel passes instead of one CTA
+// walking the columns.  All intermediate arithmetic is fp64, so a single pass keeps |Q^T Q - I| at fp32 rounding
+// level up to cond(X) ~ 1e6 (Gram error ~ cond^2 * 2^-53):
+//     G = X^T X (fp64, all SMs)  ->  G = L L^T (one CTA)  ->  q_row . L^T = x_row by forward substitution (all SMs)
+// R = L^T has a positive diagonal: same sign convention as the CGS2 kernel.  A column whose pivot vanishes
+// (d_j <= 1e-12 * G_jj: linearly dependent on the previous ones) yields a ZERO column of Q, like CGS2's zero-norm rule.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCqMaxR = 64;
+constexpr int kCqRows = 128;
+constexpr size_t kCqWsPerBatch = (kCqMaxR * kCqMaxR + kCqMaxR) * sizeof(double);
+
+__global__ void __launch_bounds__(256)
+cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __restrict__ ws, int m, int r) {
+  __shared__ float sx[kCqRows][kCqMaxR + 1];
+  const float* Xb = X + blockIdx.y * x_bs;
+  double* G = ws + blockIdx.y * (kCqMaxR * kCqMaxR + kCqMaxR);
+  const int row0 = blockIdx.x * kCqRows;
+  const int rows = min(kCqRows, m - row0);
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < rows * r; idx += 256) {
+    const int i = idx / r, k = idx - i * r;
+    sx[i][k] = Xb[static_cast<int64_t>(row0 + i) * ldx + k];
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;   // G[ty + 16a][tx + 16c]
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+  for (int i = 0; i < rows; ++i) {
+    double xa[4], xc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xa[a] = (ty + 16 * a < r) ? static_cast<double>(sx[i][ty + 16 * a]) : 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xc[c] = (tx + 16 * c < r) ? static_cast<double>(sx[i][tx + 16 * c]) : 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = fma(xa[a], xc[c], acc[a][c]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = ty + 16 * a, j = tx + 16 * c;
+      if (i < r && j < r && j <= i) atomicAdd(&G[i * kCqMaxR + j], acc[a][c]);   // lower triangle is enough
+    }
+}
+
+// In place: lower triangle of G -> L; dinv[j] = 1 / L_jj (0 for a dependent column).  1024 threads, 4 entries each.
+__global__ void __launch_bounds__(1024)
+cq_chol_kernel(double* __restrict__ ws, int r) {
+  __shared__ double A[kCqMaxR][kCqMaxR + 1];
+  __shared__ double g0[kCqMaxR];
+  __shared__ double piv;       // L_jj of the current step (0 if dependent)
+  double* G = ws + blockIdx.x * (kCqMaxR * kCqMaxR + kCqMaxR);
+  double* dinv = G + kCqMaxR * kCqMaxR;
+  const int tid = threadIdx.x;
+  const int i = tid >> 4, kb = tid & 15;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int k = kb + 16 * c;
+    A[i][k] = (i < r && k <= i) ? G[i * kCqMaxR + k] : 0.0;
+  }
+  __syncthreads();
+  if (tid < kCqMaxR) g0[tid] = A[tid][tid];
+  __syncthreads();
+  for (int j = 0; j < r; ++j) {
+    if (tid == 0) {
+      const double d = A[j][j];
+      const bool alive = (g0[j] > 1e-300) && (d > 1e-12 * g0[j]);
+      piv = alive ? sqrt(d) : 0.0;
+    }
+    __syncthreads();
+    const double ljj = piv;
+    const double inv = ljj > 0.0 ? 1.0 / ljj : 0.0;
+    if (tid > j && tid < r) A[tid][j] *= inv;            // column j of L (zero if dependent)
+    if (tid == 0) {
+      A[j][j] = ljj;
+      dinv[j] = inv;
+    }
+    __syncthreads();
+    if (i > j && i < r) {
+      const double lij = A[i][j];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = kb + 16 * c;
+        if (k > j && k <= i) A[i][k] -= lij * A[k][j];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int k = kb + 16 * c;
+    if (i < r && k <= i) G[i * kCqMaxR + k] = A[i][k];
+  }
+}
+
+// Q[row, :] = x_row . R^-1 with R = L^T:  q_j = (x_j - sum_{k<j} q_k L_jk) * dinv_j, one row per thread, fp64.
+__global__ void __launch_bounds__(kCqRows)
+cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __restrict__ Q, int64_t q_bs,
+                const double* __restrict__ ws, int m, int r) {
+  extern __shared__ double cq_smem[];
+  double (*sL)[kCqMaxR + 1] = reinterpret_cast<double (*)[kCqMaxR + 1]>(cq_smem);   // sL[k][j] = L_jk (broadcast reads)
+  double* sdinv = cq_smem + kCqMaxR * (kCqMaxR + 1);
+  float (*sx)[kCqMaxR + 1] = reinterpret_cast<float (*)[kCqMaxR + 1]>(sdinv + kCqMaxR);
+  const double* G = ws + blockIdx.y * (kCqMaxR * kCqMaxR + kCqMaxR);
+  const float* Xb = X + blockIdx.y * x_bs;
+  float* Qb = Q + blockIdx.y * q_bs;
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * kCqRows;
+  const int rows = min(kCqRows, m - row0);
+  for (int idx = tid; idx < r * r; idx += kCqRows) {
+    const int j = idx / r, k = idx - j * r;
+    sL[k][j] = (k <= j) ? G[j * kCqMaxR + k] : 0.0;
+  }
+  if (tid < r) sdinv[tid] = G[kCqMaxR * kCqMaxR + tid];
+  for (int idx = tid; idx < rows * r; idx += kCqRows) {
+    const int i = idx / r, k = idx - i * r;
+    sx[i][k] = Xb[static_cast<int64_t>(row0 + i) * ldx + k];
+  }
+  __syncthreads();
+  if (tid < rows) {
+    double q[kCqMaxR];
+#pragma unroll
+    for (int j = 0; j < kCqMaxR; ++j) {
+      q[j] = 0.0;
+      if (j < r) {
+        double acc = static_cast<double>(sx[tid][j]);
+#pragma unroll
+        for (int k = 0; k < j; ++k) acc = fma(-q[k], sL[k][j], acc);
+        q[j] = acc * sdinv[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kCqMaxR; ++j)
+      if (j < r) sx[tid][j] = static_cast<float>(q[j]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < rows * r; idx += kCqRows) {
+    const int i = idx / r, k = idx - i * r;
+    Qb[static_cast<int64_t>(row0 + i) * r + k] = sx[i][k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // projection R[r, n] = Q[m, r]^T L[m, n]    (fp32, register-tiled; split over m with fp32 red.add)
 // ------------------------------------------------------------------------------------------------
 constexpr int kPjTN = 128;   // columns of L per CTA
@@ -150,12 +298,14 @@ constexpr int kPjTM = 32;    // rows of L per smem stage
 constexpr int kPjThreads = 256;
 constexpr int kPjRT = 64;    // rank tile
 
-// thread layout: 16 (r) x 16 (n); each thread owns 4 (r) x 8 (n) outputs of a 64 x 128 tile
+// thread layout: 16 (r) x 16 (n); each thread owns 4 (r) x (4 + 4) (n) outputs of a 64 x 128 tile: rank rows
+// tr*4..+3, columns tn*4..+3 and 64+tn*4..+3, so that every shared-memory operand is one conflict-free 16-byte load
+// (3 LDS.128 per 32 FMA: FMA-bound, not LDS-bound).  The next K stage is prefetched into registers during the FMAs.
 __global__ void __launch_bounds__(kPjThreads)
 tt_project_kernel(const float* __restrict__ L, int64_t l_bs, const float* __restrict__ Q, int64_t q_bs,
                   float* __restrict__ R, int64_t r_bs, int m, int n, int r, int m_per_split) {
-  __shared__ float sL[kPjTM][kPjTN];
-  __shared__ float sQ[kPjTM][kPjRT + 1];
+  __shared__ __align__(16) float sL[kPjTM][kPjTN];
+  __shared__ __align__(16) float sQ[kPjTM][kPjRT];
   const int b = blockIdx.z;
   const float* Lb = L + b * l_bs;
   const float* Qb = Q + b * q_bs;
@@ -165,32 +315,68 @@ tt_project_kernel(const float* __restrict__ L, int64_t l_bs, const float* __rest
   const int m_end = min(m, m_begin + m_per_split);
   const int tid = threadIdx.x;
   const int tr = tid / 16, tn = tid % 16;
+  const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(Lb) & 15) == 0);
+  // staging assignment: L tile = 32 rows x 32 float4 -> 4 float4 per thread; Q tile = 32 x 64 floats -> 8 per thread
+  float4 pl[4];
+  float pq[8];
   for (int r0 = 0; r0 < r; r0 += kPjRT) {
     float acc[4][8];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
-    for (int mm0 = m_begin; mm0 < m_end; mm0 += kPjTM) {
-      // stage L[mm0:mm0+32, n0:n0+128] and Q[mm0:mm0+32, r0:r0+64]
-      for (int idx = tid; idx < kPjTM * kPjTN; idx += kPjThreads) {
-        const int i = idx / kPjTN, c = idx % kPjTN;
-        const int gi = mm0 + i, gc = n0 + c;
-        sL[i][c] = (gi < m_end && gc < n) ? Lb[static_cast<int64_t>(gi) * n + gc] : 0.f;
+    auto fetch = [&](int mm0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = tid + u * kPjThreads;          // 0..1023
+        const int i = idx >> 5, c4 = (idx & 31) * 4;
+        const int gi = mm0 + i, gc = n0 + c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gi < m_end) {
+          const float* src = Lb + static_cast<int64_t>(gi) * n + gc;
+          if (vec && gc + 3 < n) {
+            v = *reinterpret_cast<const float4*>(src);
+          } else {
+            if (gc < n) v.x = src[0];
+            if (gc + 1 < n) v.y = src[1];
+            if (gc + 2 < n) v.z = src[2];
+            if (gc + 3 < n) v.w = src[3];
+          }
+        }
+        pl[u] = v;
       }
-      for (int idx = tid; idx < kPjTM * kPjRT; idx += kPjThreads) {
-        const int i = idx / kPjRT, k = idx % kPjRT;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = tid + u * kPjThreads;          // 0..2047
+        const int i = idx >> 6, k = idx & 63;
         const int gi = mm0 + i, gk = r0 + k;
-        sQ[i][k] = (gi < m_end && gk < r) ? Qb[static_cast<int64_t>(gi) * r + gk] : 0.f;
+        pq[u] = (gi < m_end && gk < r) ? Qb[static_cast<int64_t>(gi) * r + gk] : 0.f;
       }
+    };
+    auto stash = [&]() {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = tid + u * kPjThreads;
+        *reinterpret_cast<float4*>(&sL[idx >> 5][(idx & 31) * 4]) = pl[u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = tid + u * kPjThreads;
+        sQ[idx >> 6][idx & 63] = pq[u];
+      }
+    };
+    if (m_begin < m_end) fetch(m_begin);
+    for (int mm0 = m_begin; mm0 < m_end; mm0 += kPjTM) {
+      stash();
       __syncthreads();
+      if (mm0 + kPjTM < m_end) fetch(mm0 + kPjTM);
 #pragma unroll 8
       for (int i = 0; i < kPjTM; ++i) {
-        float qv[4], lv[8];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) qv[a] = sQ[i][tr * 4 + a];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) lv[c] = sL[i][tn + 16 * c];
+        const float4 q = *reinterpret_cast<const float4*>(&sQ[i][tr * 4]);
+        const float4 l0 = *reinterpret_cast<const float4*>(&sL[i][tn * 4]);
+        const float4 l1 = *reinterpret_cast<const float4*>(&sL[i][64 + tn * 4]);
+        const float qv[4] = {q.x, q.y, q.z, q.w};
+        const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -204,7 +390,7 @@ tt_project_kernel(const float* __restrict__ L, int64_t l_bs, const float* __rest
       if (gr >= r) continue;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const int gc = n0 + tn + 16 * c;
+        const int gc = n0 + (c < 4 ? tn * 4 + c : 64 + tn * 4 + (c - 4));
         if (gc < n) {
           if (gridDim.y == 1) Rb[static_cast<int64_t>(gr) * n + gc] = acc[a][c];
           else atomicAdd(&Rb[static_cast<int64_t>(gr) * n + gc], acc[a][c]);
@@ -236,8 +422,75 @@ __device__ __forceinline__ void store_from_f32<__nv_bfloat16>(__nv_bfloat16* p, 
   p[i] = __float2bfloat16(v);
 }
 
-__device__ __forceinline__ void decode_interleaved(int64_t idx, int mm, int nn, int order, int64_t& row, int64_t& col) {
+// 4 consecutive elements at an index that is a multiple of 4 (8-byte bf16 / 16-byte fp32 accesses)
+template <typename T>
+__device__ __forceinline__ void load4_as_f32(const T* p, int64_t i, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4_as_f32<float>(const float* p, int64_t i, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p + i);
+  v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4_as_f32<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p + i);
+  v[0] = __uint_as_float(t.x << 16), v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16), v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+template <typename T>
+__device__ __forceinline__ void store4_from_f32(T* p, int64_t i, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void store4_from_f32<float>(float* p, int64_t i, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p + i) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store4_from_f32<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, const float (&v)[4]) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&lo);
+  t.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p + i) = t;
+}
+
+// Division of a 32-bit index by a run-time constant d (>= 1) without the ~25-instruction software divide:
+// q = (mulhi(n, M) + n) >> s with s = ceil(log2 d), M = floor(2^32 * (2^s - d) / d) + 1 (exact for all 32-bit n).
+struct FastDiv {
+  uint32_t d, M, s;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((uint64_t(1) << s) < d) ++s;
+  f.s = s;
+  f.M = static_cast<uint32_t>(((uint64_t(1) << 32) * ((uint64_t(1) << s) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return static_cast<uint32_t>((static_cast<uint64_t>(__umulhi(n, f.M)) + n) >> f.s);
+}
+
+__device__ __forceinline__ void decode_interleaved(uint32_t idx, const FastDiv& fm, const FastDiv& fn, int order,
+                                                   int64_t& row, int64_t& col) {
   // idx = ((((i1*nn + o1)*mm + i2)*nn + o2) ... ); peel digits from the least significant end
+  int64_t rmul = 1, cmul = 1;
+  row = 0;
+  col = 0;
+  for (int k = 0; k < order; ++k) {
+    uint32_t q = fdiv(idx, fn);
+    const uint32_t o = idx - q * fn.d;
+    idx = q;
+    q = fdiv(idx, fm);
+    const uint32_t i = idx - q * fm.d;
+    idx = q;
+    row += i * rmul;
+    col += o * cmul;
+    rmul *= fm.d;
+    cmul *= fn.d;
+  }
+}
+
+// generic (64-bit index) variant for tensors with >= 2^32 padded elements
+__device__ __forceinline__ void decode_interleaved64(int64_t idx, int mm, int nn, int order, int64_t& row, int64_t& col) {
   int64_t rmul = 1, cmul = 1;
   row = 0;
   col = 0;
@@ -254,23 +507,27 @@ __device__ __forceinline__ void decode_interleaved(int64_t idx, int mm, int nn, 
 }
 
 template <typename T>
-__global__ void tt_interleave_kernel(const T* __restrict__ src, int M, int N, int mm, int nn, int order,
+__global__ void tt_interleave_kernel(const T* __restrict__ src, int M, int N, FastDiv fm, FastDiv fn, int order,
                                      float* __restrict__ out, int64_t total) {
+  const bool small = total < (int64_t(1) << 32);
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     int64_t row, col;
-    decode_interleaved(idx, mm, nn, order, row, col);
+    if (small) decode_interleaved(static_cast<uint32_t>(idx), fm, fn, order, row, col);
+    else decode_interleaved64(idx, fm.d, fn.d, order, row, col);
     out[idx] = (row < M && col < N) ? load_as_f32<T>(src, row * N + col) : 0.f;
   }
 }
 
 template <typename T>
-__global__ void tt_deinterleave_kernel(const float* __restrict__ src, int M, int N, int mm, int nn, int order,
+__global__ void tt_deinterleave_kernel(const float* __restrict__ src, int M, int N, FastDiv fm, FastDiv fn, int order,
                                        T* __restrict__ out, int64_t total) {
+  const bool small = total < (int64_t(1) << 32);
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     int64_t row, col;
-    decode_interleaved(idx, mm, nn, order, row, col);
+    if (small) decode_interleaved(static_cast<uint32_t>(idx), fm, fn, order, row, col);
+    else decode_interleaved64(idx, fm.d, fn.d, order, row, col);
     if (row < M && col < N) store_from_f32<T>(out, row * N + col, src[idx]);
   }
 }
@@ -334,15 +591,16 @@ tt_adam_fused2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* _
                       const float* __restrict__ G2m, const float* __restrict__ G1v, const float* __restrict__ G2v,
                       int r, float* __restrict__ m_out, float* __restrict__ v_out, int M, int N, int mm, int nn,
                       float beta1, float omb1, float beta2, float omb2, float eps, float step_size, float lr_wd, int first_step) {
-  extern __shared__ float fs[];
+  extern __shared__ __align__(16) float fs[];
   const int P = mm * nn;  // interleaved matrix is P x P
-  // smem: G1m tile [64][r+1], G1v tile [64][r+1], G2m tile [r][64], G2v tile [r][64]
+  // smem, all k-major so that every operand of the inner product is one 16-byte load:
+  //   s1m/s1v [r][64] = G1[a0 + i][k] transposed,  s2m/s2v [r][64] = G2[k][b0 + c]
   float* s1m = fs;
-  float* s1v = s1m + 64 * (r + 1);
-  float* s2m = s1v + 64 * (r + 1);
+  float* s1v = s1m + r * 64;
+  float* s2m = s1v + r * 64;
   float* s2v = s2m + r * 64;
   const int a0 = blockIdx.y * 64, b0 = blockIdx.x * 64;
-  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;   // thread owns rows ty*4..+3, columns tx*4..+3
   float am[4][4], av[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -352,26 +610,22 @@ tt_adam_fused2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* _
     for (int idx = tid; idx < 64 * r; idx += 256) {
       const int i = idx / r, k = idx % r;
       const bool ok = a0 + i < P;
-      s1m[i * (r + 1) + k] = ok ? G1m[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
-      s1v[i * (r + 1) + k] = ok ? G1v[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+      s1m[k * 64 + i] = ok ? G1m[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+      s1v[k * 64 + i] = ok ? G1v[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
       const int kk = idx / 64, c = idx % 64;
       const bool ok2 = b0 + c < P;
       s2m[kk * 64 + c] = ok2 ? G2m[static_cast<int64_t>(kk) * P + b0 + c] : 0.f;
       s2v[kk * 64 + c] = ok2 ? G2v[static_cast<int64_t>(kk) * P + b0 + c] : 0.f;
     }
     __syncthreads();
+#pragma unroll 4
     for (int k = 0; k < r; ++k) {
-      float x1m[4], x1v[4], x2m[4], x2v[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        x1m[a] = s1m[(ty * 4 + a) * (r + 1) + k];
-        x1v[a] = s1v[(ty * 4 + a) * (r + 1) + k];
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        x2m[c] = s2m[k * 64 + tx + 16 * c];
-        x2v[c] = s2v[k * 64 + tx + 16 * c];
-      }
+      const float4 a1m = *reinterpret_cast<const float4*>(s1m + k * 64 + ty * 4);
+      const float4 a1v = *reinterpret_cast<const float4*>(s1v + k * 64 + ty * 4);
+      const float4 b2m = *reinterpret_cast<const float4*>(s2m + k * 64 + tx * 4);
+      const float4 b2v = *reinterpret_cast<const float4*>(s2v + k * 64 + tx * 4);
+      const float x1m[4] = {a1m.x, a1m.y, a1m.z, a1m.w}, x1v[4] = {a1v.x, a1v.y, a1v.z, a1v.w};
+      const float x2m[4] = {b2m.x, b2m.y, b2m.z, b2m.w}, x2v[4] = {b2v.x, b2v.y, b2v.z, b2v.w};
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -388,7 +642,7 @@ tt_adam_fused2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* _
     const int i1 = ga / nn, o1 = ga % nn;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int gb = b0 + tx + 16 * c;
+      const int gb = b0 + tx * 4 + c;
       if (gb >= P) continue;
       const int i2 = gb / nn, o2 = gb % nn;
       const int64_t row = static_cast<int64_t>(i1) * mm + i2, col = static_cast<int64_t>(o1) * nn + o2;
@@ -407,6 +661,243 @@ tt_adam_fused2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* _
       }
       m_out[static_cast<int64_t>(ga) * P + gb] = mo;
       v_out[static_cast<int64_t>(ga) * P + gb] = vo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Order-2 TT-Adam with the re-compression fused in (no dense moment ever reaches HBM).
+//
+//   new moments  m' = b1 * (G1m . G2m) + (1-b1) g,   v' = b2 * max(G1v . G2v, 0) + (1-b2) g^2   (P x P, interleaved)
+//   new cores    Q' = thin-QR(first r columns of m' / v'),   R' = Q'^T m' / Q'^T v'
+//
+// HEAD : the first 64 columns of m', v' (P x 64 each) -> X, the input of the thin QR.  p is NOT touched.
+// FULL : CTA = (strip of 64 columns, range of 64-row tiles).  Per tile: reconstruct the old moments from the cores
+//        (register-tiled rank-R product), Adam on p, stash m', v' in shared memory, accumulate R'[:, strip] +=
+//        Q'[tile rows]^T . tile in registers; one fp32 red.add of the accumulators per CTA at the end.
+// Traffic per step: g once + p read/write + cores (vs. + 16 B/element for dense fp32 moments written and re-read).
+// R = rank padded to 8/16/32/64 (cores and bases are zero-padded in shared memory).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int R, bool HEAD>
+__global__ void __launch_bounds__(256, (R <= 16 ? 4 : (R <= 32 ? 3 : 2)))
+tt_adam2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __restrict__ G1m, const float* __restrict__ G2m,
+                const float* __restrict__ G1v, const float* __restrict__ G2v, int r, const float* __restrict__ Qm,
+                const float* __restrict__ Qv, float* __restrict__ Rm, float* __restrict__ Rv, float* __restrict__ Xm,
+                float* __restrict__ Xv, int M, int N, int mm, int nn, float beta1, float omb1, float beta2, float omb2,
+                float eps, float step_size, float lr_wd, int first_step, int tiles_per_cta) {
+  extern __shared__ __align__(16) float fs[];
+  const int P = mm * nn;
+  float* s2m = fs;                 // [R][64]  G2m[k][b0 + c]
+  float* s2v = s2m + R * 64;
+  float* s1m = s2v + R * 64;       // [64][R]  G1m[a0 + i][k]
+  float* s1v = s1m + R * 64;
+  float* sQm = s1v + R * 64;       // [64][R]  Q'm[a0 + i][k]
+  float* sQv = sQm + 64 * R;
+  // [64][64] m' / v' tiles; at R = 64 they alias s1m / s1v (dead once the tile is reconstructed): 96 KB -> 2 CTAs per SM
+  constexpr bool kAlias = (R == 64);
+  float* sMt = kAlias ? s1m : sQv + 64 * R;
+  float* sVt = sMt + 64 * 64;
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;   // phase 1: rows ty*4..+3, columns tx*4..+3
+  const int b0 = HEAD ? 0 : blockIdx.x * 64;
+  const int n_tiles = (P + 63) / 64;
+  const int t_begin = HEAD ? blockIdx.x : blockIdx.y * tiles_per_cta;
+  const int t_end = HEAD ? blockIdx.x + 1 : min(n_tiles, t_begin + tiles_per_cta);
+  // phase 2 mapping: column pcol of the strip, quarter kpart of the padded rank
+  const int pcol = tid & 63, kpart = tid >> 6;
+  constexpr int KQ = R / 4;
+  float accm[KQ], accv[KQ];
+#pragma unroll
+  for (int k = 0; k < KQ; ++k) accm[k] = accv[k] = 0.f;
+  // element (ga, gb) of the interleaved matrix is (row, col) = (i1*mm + i2, o1*nn + o2) with ga = i1*nn + o1 and
+  // gb = i2*nn + o2: the column part depends on the strip only, so it is decoded once per CTA
+  int ci2[4], co2[4];
+  int64_t colbase[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int gb = b0 + tx * 4 + c;
+    ci2[c] = gb / nn;
+    co2[c] = gb - ci2[c] * nn;
+    colbase[c] = static_cast<int64_t>(ci2[c]) * N + co2[c];
+    if (gb >= P) ci2[c] = 1 << 28;   // fails the row bound below
+  }
+  const bool cols_contig = (ci2[0] == ci2[3]);
+
+  if (!first_step) {
+    for (int idx = tid; idx < R * 64; idx += 256) {
+      const int kk = idx / 64, c = idx % 64;
+      const bool ok = kk < r && b0 + c < P;
+      s2m[idx] = ok ? G2m[static_cast<int64_t>(kk) * P + b0 + c] : 0.f;
+      s2v[idx] = ok ? G2v[static_cast<int64_t>(kk) * P + b0 + c] : 0.f;
+    }
+  }
+  for (int t = t_begin; t < t_end; ++t) {
+    const int a0 = t * 64;
+    __syncthreads();   // previous tile's phase 2 is done with sQ / sMt; first iteration: s2 staged
+    // staging: constant trip counts, so all global loads of a tile are in flight before the first shared store
+    constexpr int kStage = 64 * R / 256;
+    if (!first_step) {
+      float t1m[kStage], t1v[kStage];
+#pragma unroll
+      for (int u = 0; u < kStage; ++u) {
+        const int idx = tid + u * 256;
+        const int i = idx / R, k = idx % R;
+        const bool ok = a0 + i < P && k < r;
+        t1m[u] = ok ? G1m[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+        t1v[u] = ok ? G1v[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kStage; ++u) {
+        s1m[tid + u * 256] = t1m[u];      // row-major [64][R], like G1 itself
+        s1v[tid + u * 256] = t1v[u];
+      }
+    }
+    if (!HEAD) {
+      float tqm[kStage], tqv[kStage];
+#pragma unroll
+      for (int u = 0; u < kStage; ++u) {
+        const int idx = tid + u * 256;
+        const int i = idx / R, k = idx % R;
+        const bool ok = a0 + i < P && k < r;
+        tqm[u] = ok ? Qm[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+        tqv[u] = ok ? Qv[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kStage; ++u) {
+        sQm[tid + u * 256] = tqm[u];
+        sQv[tid + u * 256] = tqv[u];
+      }
+    }
+    __syncthreads();
+    float am[4][4], av[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) am[a][c] = av[a][c] = 0.f;
+    if (!first_step) {
+#pragma unroll 2
+      for (int k0 = 0; k0 < R; k0 += 4) {
+        float x1m[4][4], x1v[4][4], x2m[4][4], x2v[4][4];   // [row a | k j][k j | col c]
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float4 tm = *reinterpret_cast<const float4*>(s1m + (ty * 4 + a) * R + k0);
+          const float4 tv = *reinterpret_cast<const float4*>(s1v + (ty * 4 + a) * R + k0);
+          x1m[a][0] = tm.x, x1m[a][1] = tm.y, x1m[a][2] = tm.z, x1m[a][3] = tm.w;
+          x1v[a][0] = tv.x, x1v[a][1] = tv.y, x1v[a][2] = tv.z, x1v[a][3] = tv.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 tm = *reinterpret_cast<const float4*>(s2m + (k0 + j) * 64 + tx * 4);
+          const float4 tv = *reinterpret_cast<const float4*>(s2v + (k0 + j) * 64 + tx * 4);
+          x2m[j][0] = tm.x, x2m[j][1] = tm.y, x2m[j][2] = tm.z, x2m[j][3] = tm.w;
+          x2v[j][0] = tv.x, x2v[j][1] = tv.y, x2v[j][2] = tv.z, x2v[j][3] = tv.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              am[a][c] = fmaf(x1m[a][j], x2m[j][c], am[a][c]);
+              av[a][c] = fmaf(x1v[a][j], x2v[j][c], av[a][c]);
+            }
+      }
+    }
+    if (kAlias && !HEAD) __syncthreads();   // every thread is done reading s1m / s1v before the tile overwrites them
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int ga = a0 + ty * 4 + a;
+      const int i1 = ga / nn, o1 = ga - i1 * nn;
+      const int64_t rowbase = static_cast<int64_t>(i1) * mm * N + static_cast<int64_t>(o1) * nn;
+      const int rlim = (ga < P) ? M - i1 * mm : 0;     // valid iff i2 < rlim
+      const int clim = N - o1 * nn;                    // valid iff o2 < clim
+      float mo4[4] = {0.f, 0.f, 0.f, 0.f}, vo4[4] = {0.f, 0.f, 0.f, 0.f};
+      bool ok[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ok[c] = ci2[c] < rlim && co2[c] < clim;
+      const int64_t e0 = rowbase + colbase[0];
+      float gv[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool vec = cols_contig && ok[0] && ok[3] && ((e0 & 3) == 0);
+      if (vec) {
+        load4_as_f32<T>(g, e0, gv);
+        if (!HEAD) load4_as_f32<T>(p, e0, pv);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (ok[c]) {
+            gv[c] = load_as_f32<T>(g, rowbase + colbase[c]);
+            if (!HEAD) pv[c] = load_as_f32<T>(p, rowbase + colbase[c]);
+          }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (ok[c]) {
+          const float mp = am[a][c];
+          const float vp = fmaxf(av[a][c], 0.f);                       // ttadam.py:84
+          const float mo = beta1 * mp + omb1 * gv[c];                  // ttadam.py:92
+          const float vo = beta2 * vp + omb2 * gv[c] * gv[c];          // ttadam.py:93
+          if (!HEAD) {
+            pv[c] -= step_size * (mo / (sqrtf(vo) + eps));             // ttadam.py:94,103,108
+            if (lr_wd > 0.f) pv[c] -= lr_wd * pv[c];                   // ttadam.py:110-111
+          }
+          mo4[c] = mo;
+          vo4[c] = vo;
+        }
+      }
+      if (!HEAD) {
+        if (vec) {
+          store4_from_f32<T>(p, e0, pv);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (ok[c]) store_from_f32<T>(p, rowbase + colbase[c], pv[c]);
+        }
+      }
+      if (HEAD) {
+        if (ga < P) {
+          *reinterpret_cast<float4*>(Xm + static_cast<int64_t>(ga) * 64 + tx * 4) = make_float4(mo4[0], mo4[1], mo4[2], mo4[3]);
+          *reinterpret_cast<float4*>(Xv + static_cast<int64_t>(ga) * 64 + tx * 4) = make_float4(vo4[0], vo4[1], vo4[2], vo4[3]);
+        }
+      } else {
+        *reinterpret_cast<float4*>(sMt + (ty * 4 + a) * 64 + tx * 4) = make_float4(mo4[0], mo4[1], mo4[2], mo4[3]);
+        *reinterpret_cast<float4*>(sVt + (ty * 4 + a) * 64 + tx * 4) = make_float4(vo4[0], vo4[1], vo4[2], vo4[3]);
+      }
+    }
+    if (!HEAD) {
+      __syncthreads();
+      // phase 2: R'[k, b0 + pcol] += sum_i Q'[a0 + i, k] * tile[i, pcol]
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) {
+        const float mv = sMt[i * 64 + pcol], vv = sVt[i * 64 + pcol];
+        float qm[KQ], qv[KQ];
+        if constexpr (KQ >= 4) {
+#pragma unroll
+          for (int k4 = 0; k4 < KQ / 4; ++k4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(sQm + i * R + kpart * KQ + 4 * k4);
+            const float4 b4 = *reinterpret_cast<const float4*>(sQv + i * R + kpart * KQ + 4 * k4);
+            qm[4 * k4] = a4.x, qm[4 * k4 + 1] = a4.y, qm[4 * k4 + 2] = a4.z, qm[4 * k4 + 3] = a4.w;
+            qv[4 * k4] = b4.x, qv[4 * k4 + 1] = b4.y, qv[4 * k4 + 2] = b4.z, qv[4 * k4 + 3] = b4.w;
+          }
+        } else {
+          const float2 a2 = *reinterpret_cast<const float2*>(sQm + i * R + kpart * KQ);
+          const float2 b2 = *reinterpret_cast<const float2*>(sQv + i * R + kpart * KQ);
+          qm[0] = a2.x, qm[1] = a2.y, qv[0] = b2.x, qv[1] = b2.y;
+        }
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+          accm[k] = fmaf(qm[k], mv, accm[k]);
+          accv[k] = fmaf(qv[k], vv, accv[k]);
+        }
+      }
+    }
+  }
+  if (!HEAD && b0 + pcol < P) {
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int gk = kpart * KQ + k;
+      if (gk < r) {
+        atomicAdd(Rm + static_cast<int64_t>(gk) * P + b0 + pcol, accm[k]);
+        atomicAdd(Rv + static_cast<int64_t>(gk) * P + b0 + pcol, accv[k]);
+      }
     }
   }
 }
@@ -435,11 +926,94 @@ static inline int grid_for(int64_t n, int threads) {
   return static_cast<int>(std::min<int64_t>(b, int64_t(num_sms()) * 16));
 }
 
+
+template <typename T, int R>
+static int launch_adam2(bool head, void* p, const void* g, const float* G1m, const float* G2m, const float* G1v,
+                        const float* G2v, int r, const float* Qm, const float* Qv, float* Rm, float* Rv, float* Xm,
+                        float* Xv, int M, int N, int mm, int nn, float beta1, float omb1, float beta2, float omb2, float eps,
+                        float step_size, float lr_wd, int first_step, cudaStream_t stream) {
+  const int P = mm * nn;
+  const int n_tiles = ceil_div(P, 64);
+  const size_t smem = (size_t(4) * R * 64 + size_t(2) * 64 * R + (R == 64 ? 0 : size_t(2) * 64 * 64)) * sizeof(float);
+  if (head) {
+    auto k = tt_adam2_kernel<T, R, true>;
+    SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k<<<n_tiles, 256, smem, stream>>>(static_cast<T*>(p), static_cast<const T*>(g), G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, Xm,
+                                      Xv, M, N, mm, nn, beta1, omb1, beta2, omb2, eps, step_size, lr_wd, first_step, 1);
+  } else {
+    // strips x row-ranges: enough CTAs that every SM holds as many as its shared memory admits (the per-tile chain
+    // load -> reconstruct -> update -> project is latency-bound inside one CTA); every CTA red.adds its [r x 64]
+    // accumulators once
+    const int ctas_per_sm = std::max(1, std::min(R <= 16 ? 4 : (R <= 32 ? 3 : 2), int(size_t(220) * 1024 / smem)));
+    int splits = std::max(1, (2 * ctas_per_sm * num_sms()) / n_tiles);
+    splits = std::min(splits, n_tiles);
+    const int per = ceil_div(n_tiles, splits);
+    splits = ceil_div(n_tiles, per);
+    auto k = tt_adam2_kernel<T, R, false>;
+    SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k<<<dim3(n_tiles, splits), 256, smem, stream>>>(static_cast<T*>(p), static_cast<const T*>(g), G1m, G2m, G1v, G2v, r, Qm,
+                                                    Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1, beta2, omb2, eps,
+                                                    step_size, lr_wd, first_step, per);
+  }
+  SOWB_CHECK_CUDA(cudaGetLastError());
+  return SOWB_OK;
+}
+
+template <typename T>
+static int dispatch_adam2(bool head, void* p, const void* g, const float* G1m, const float* G2m, const float* G1v,
+                          const float* G2v, int r, const float* Qm, const float* Qv, float* Rm, float* Rv, float* Xm,
+                          float* Xv, int M, int N, int mm, int nn, float beta1, float omb1, float beta2, float omb2,
+                          float eps, float step_size, float lr_wd, int first_step, cudaStream_t stream) {
+#define SOWB_ADAM2(RR)                                                                                                \
+  return launch_adam2<T, RR>(head, p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1,     \
+                             beta2, omb2, eps, step_size, lr_wd, first_step, stream)
+  if (r <= 8) SOWB_ADAM2(8);
+  if (r <= 16) SOWB_ADAM2(16);
+  if (r <= 32) SOWB_ADAM2(32);
+  SOWB_ADAM2(64);
+#undef SOWB_ADAM2
+}
+
 }  // namespace sowb
 
 using namespace sowb;
 
 extern "C" {
+
+static int adam2_common(bool head, void* p, const void* g, const float* G1m, const float* G2m, const float* G1v,
+                        const float* G2v, int r, const float* Qm, const float* Qv, float* Rm, float* Rv, float* Xm,
+                        float* Xv, int M, int N, int mm, int nn, double beta1_d, double beta2_d, double eps_d,
+                        double step_size_d, double lr_wd_d, int first_step, int dtype, void* stream_) {
+  const float beta1 = float(beta1_d), beta2 = float(beta2_d), omb1 = float(1.0 - beta1_d), omb2 = float(1.0 - beta2_d);
+  SOWB_REQUIRE(g != nullptr, "tt_adam2: null gradient pointer");
+  SOWB_REQUIRE(first_step || (G1m && G2m && G1v && G2v), "tt_adam2: null core pointer");
+  SOWB_REQUIRE(r > 0 && r <= 64, "tt_adam2: rank %d unsupported (1..64)", r);
+  SOWB_REQUIRE(int64_t(mm) * mm >= M && int64_t(nn) * nn >= N, "tt_adam2: mm/nn too small for (M,N)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (dtype == SOWB_BF16)
+    return dispatch_adam2<__nv_bfloat16>(head, p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1,
+                                         beta2, omb2, float(eps_d), float(step_size_d), float(lr_wd_d), first_step, stream);
+  if (dtype == SOWB_F32)
+    return dispatch_adam2<float>(head, p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1, beta2,
+                                 omb2, float(eps_d), float(step_size_d), float(lr_wd_d), first_step, stream);
+  return set_error(SOWB_EINVAL, "tt_adam2: unknown dtype %d", dtype);
+}
+
+int tt_adam2_head(const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r, float* Xm,
+                  float* Xv, int M, int N, int mm, int nn, double beta1, double beta2, int first_step, int dtype,
+                  void* stream) {
+  SOWB_REQUIRE(Xm && Xv, "tt_adam2_head: null output pointer");
+  return adam2_common(true, nullptr, g, G1m, G2m, G1v, G2v, r, nullptr, nullptr, nullptr, nullptr, Xm, Xv, M, N, mm, nn,
+                      beta1, beta2, 0.0, 0.0, 0.0, first_step, dtype, stream);
+}
+
+int tt_adam2_fused(void* p, const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r,
+                   const float* Qm, const float* Qv, float* Rm, float* Rv, int M, int N, int mm, int nn, double beta1,
+                   double beta2, double eps, double step_size, double lr_wd, int first_step, int dtype, void* stream) {
+  SOWB_REQUIRE(p && Qm && Qv && Rm && Rv, "tt_adam2_fused: null pointer argument");
+  return adam2_common(false, p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, nullptr, nullptr, M, N, mm, nn, beta1, beta2, eps,
+                      step_size, lr_wd, first_step, dtype, stream);
+}
 
 int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64_t q_batch_stride, int m, int r,
                 int batch, void* ws, size_t ws_bytes, void* stream_) {
@@ -450,6 +1024,22 @@ int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t need = size_t(batch) * m * r * sizeof(float);
   if (ws_bytes < need) return set_error(SOWB_EWORKSPACE, "sow_thin_qr: workspace %zu B < required %zu B", ws_bytes, need);
+  if (r <= kCqMaxR && m >= 64 && ws_bytes >= size_t(batch) * kCqWsPerBatch && batch <= 65535 &&
+      (reinterpret_cast<uintptr_t>(ws) & 7) == 0) {
+    // Cholesky-QR: Gram (all SMs) -> Cholesky (one CTA per matrix) -> triangular solve per row (all SMs)
+    double* wsd = static_cast<double*>(ws);
+    SOWB_CHECK_CUDA(cudaMemsetAsync(wsd, 0, size_t(batch) * kCqWsPerBatch, stream));
+    dim3 grid(ceil_div(m, kCqRows), batch);
+    cq_gram_kernel<<<grid, 256, 0, stream>>>(X, x_batch_stride, ldx, wsd, m, r);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    cq_chol_kernel<<<batch, 1024, 0, stream>>>(wsd, r);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    constexpr size_t solve_smem = (kCqMaxR * (kCqMaxR + 1) + kCqMaxR) * sizeof(double) + size_t(kCqRows) * (kCqMaxR + 1) * sizeof(float);
+    SOWB_CHECK_CUDA(cudaFuncSetAttribute(cq_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(solve_smem)));
+    cq_solve_kernel<<<grid, kCqRows, solve_smem, stream>>>(X, x_batch_stride, ldx, Q, q_batch_stride, wsd, m, r);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    return SOWB_OK;
+  }
   const size_t smem = (size_t(r) + kQrWarps * 64 + size_t(kQrWarps) * 32 * 33) * sizeof(float);
   SOWB_CHECK_CUDA(cudaFuncSetAttribute(thin_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   thin_qr_kernel<<<batch, kQrThreads, smem, stream>>>(X, x_batch_stride, ldx, Q, q_batch_stride, static_cast<float*>(ws), m, r);
@@ -489,9 +1079,9 @@ int tt_interleave(const void* src, int M, int N, int mm, int nn, int order, floa
   int64_t total = 1;
   for (int k = 0; k < order; ++k) total *= int64_t(mm) * nn;
   if (dtype == SOWB_BF16)
-    tt_interleave_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), M, N, mm, nn, order, out, total);
+    tt_interleave_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), M, N, make_fastdiv(mm), make_fastdiv(nn), order, out, total);
   else if (dtype == SOWB_F32)
-    tt_interleave_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), M, N, mm, nn, order, out, total);
+    tt_interleave_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), M, N, make_fastdiv(mm), make_fastdiv(nn), order, out, total);
   else
     return set_error(SOWB_EINVAL, "tt_interleave: unknown dtype %d", dtype);
   SOWB_CHECK_CUDA(cudaGetLastError());
@@ -505,9 +1095,9 @@ int tt_deinterleave(const float* src, int M, int N, int mm, int nn, int order, v
   int64_t total = 1;
   for (int k = 0; k < order; ++k) total *= int64_t(mm) * nn;
   if (dtype == SOWB_BF16)
-    tt_deinterleave_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(src, M, N, mm, nn, order, static_cast<__nv_bfloat16*>(out), total);
+    tt_deinterleave_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(src, M, N, make_fastdiv(mm), make_fastdiv(nn), order, static_cast<__nv_bfloat16*>(out), total);
   else if (dtype == SOWB_F32)
-    tt_deinterleave_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(src, M, N, mm, nn, order, static_cast<float*>(out), total);
+    tt_deinterleave_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(src, M, N, make_fastdiv(mm), make_fastdiv(nn), order, static_cast<float*>(out), total);
   else
     return set_error(SOWB_EINVAL, "tt_deinterleave: unknown dtype %d", dtype);
   SOWB_CHECK_CUDA(cudaGetLastError());
@@ -538,7 +1128,7 @@ int tt_adam_fused2(void* p, const void* g, const float* G1m, const float* G2m, c
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int P = mm * nn;
   dim3 grid(ceil_div(P, 64), ceil_div(P, 64));
-  const size_t smem = (size_t(2) * 64 * (r + 1) + size_t(2) * r * 64) * sizeof(float);
+  const size_t smem = size_t(4) * r * 64 * sizeof(float);
   if (dtype == SOWB_BF16) {
     auto k = tt_adam_fused2_kernel<__nv_bfloat16>;
     SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -179,7 +179,8 @@ def thin_qr(X: torch.Tensor, r: int) -> torch.Tensor:
         Xb = Xb.contiguous()
     b, m, n = Xb.shape
     Q = torch.empty((b, m, r), dtype=torch.float32, device=X.device)
-    work = torch.empty((b, r, m), dtype=torch.float32, device=X.device)  # column-major CGS2 work copy
+    # scratch: column-major CGS2 work copy (b*r*m floats) or, for r <= 64, the fp64 Gram / Cholesky block per matrix
+    work = torch.empty((max(b * r * m, b * 8448),), dtype=torch.float32, device=X.device)
     rc = lib.sow_thin_qr(_p(Xb), Xb.stride(0), Xb.stride(1), _p(Q), m * r, m, r, b, _p(work), work.numel() * 4,
                          _stream_ptr(X.device))
     check(rc, "sow_thin_qr")
@@ -264,6 +265,36 @@ def tt_adam_fused2(p, g, cores_m, cores_v, mm, nn, beta1, beta2, eps, step_size,
     check(rc, "tt_adam_fused2")
     launch_counter["kernels"] += 1
     return m_out, v_out
+
+
+def tt_adam2_step(p, g, cores_m, cores_v, mm, nn, r, beta1, beta2, eps, step_size, lr_wd, first_step):
+    """Order-2 TT-Adam with the re-compression fused in (include/sow_b200.h: tt_adam2_head / tt_adam2_fused).
+    Returns the new cores ((Qm (P,r), Rm (r,P)), (Qv, Rv)); the dense moments never reach HBM."""
+    _require_cuda(p, g)
+    lib = _lib.load()
+    M, N = p.shape
+    P = mm * nn
+    dev = p.device
+    if first_step:
+        G1m = G2m = G1v = G2v = None
+    else:
+        G1m, G2m = cores_m
+        G1v, G2v = cores_v
+    g = g.contiguous()
+    dt = _dtype_code(p.dtype)
+    st = _stream_ptr(dev)
+    X = torch.empty((2, P, 64), dtype=torch.float32, device=dev)
+    rc = lib.tt_adam2_head(_p(g), _p(G1m), _p(G2m), _p(G1v), _p(G2v), r, _p(X[0]), _p(X[1]), M, N, mm, nn,
+                           float(beta1), float(beta2), 1 if first_step else 0, dt, st)
+    check(rc, "tt_adam2_head")
+    Q = thin_qr(X, r)                                   # (2, P, r): bases of the new moments
+    R = torch.zeros((2, r, P), dtype=torch.float32, device=dev)
+    rc = lib.tt_adam2_fused(_p(p), _p(g), _p(G1m), _p(G2m), _p(G1v), _p(G2v), r, _p(Q[0]), _p(Q[1]), _p(R[0]), _p(R[1]),
+                            M, N, mm, nn, float(beta1), float(beta2), float(eps), float(step_size), float(lr_wd),
+                            1 if first_step else 0, dt, st)
+    check(rc, "tt_adam2_fused")
+    launch_counter["kernels"] += 3
+    return (Q[0], R[0]), (Q[1], R[1])
 
 
 def tt_adam_dense(p, g, m, v, beta1, beta2, eps, step_size, lr_wd):

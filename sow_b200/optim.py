@@ -100,12 +100,17 @@ class TTAdam(torch.optim.Optimizer):
                 tm, tv = state["exp_avg"], state["exp_avg_sq"]
                 cm = (tm.cores[0].reshape(P, -1).contiguous(), tm.cores[1].reshape(-1, P).contiguous())
                 cv = (tv.cores[0].reshape(P, -1).contiguous(), tv.cores[1].reshape(-1, P).contiguous())
-            m_new, v_new = ops.tt_adam_fused2(pd, g, cm, cv, mm, nn_, beta1, beta2, eps, step_size, lr_wd, first)
-            L = torch.stack([m_new, v_new])                                  # (2, P, P): one batched sweep
             if r > P:
                 raise RuntimeError(f"TT rank {r} exceeds the unfolding row count {P}")
-            Q = ops.thin_qr(L, r)
-            R = ops.project(L, Q)
+            if r <= 64:
+                # fused path: Adam + re-compression in one pass over p and g (dense moments never reach HBM)
+                (Qm, Rm), (Qv, Rv) = ops.tt_adam2_step(pd, g, cm, cv, mm, nn_, r, beta1, beta2, eps, step_size, lr_wd, first)
+                Q, R = (Qm, Qv), (Rm, Rv)
+            else:
+                m_new, v_new = ops.tt_adam_fused2(pd, g, cm, cv, mm, nn_, beta1, beta2, eps, step_size, lr_wd, first)
+                L = torch.stack([m_new, v_new])                              # (2, P, P): one batched sweep
+                Q = ops.thin_qr(L, r)
+                R = ops.project(L, Q)
             for key, b in (("exp_avg", 0), ("exp_avg_sq", 1)):
                 tt = TensorTrain(list(ranks), (mm, mm), (nn_, nn_), device=pd.device)
                 tt.cores = [Q[b].reshape(1, mm, nn_, r), R[b].reshape(r, mm, nn_, 1)]
