@@ -30,7 +30,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama_350m")
     ap.add_argument("--rank", type=int, default=50)
-    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step")
+    ap.add_argument("--batch", type=int, default=128,
+                    help="sequences per GPU per step (128 = the reference's documented pre-training recipe, readme.md:5-26)")
     ap.add_argument("--seq", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-optimizer", action="store_true")
@@ -217,13 +218,53 @@ def main():
         tms, work, n = ops.profile_read(k)
         kern[k] = {"ms_total": tms, "work": work, "launches": n}
     ops.profile_enable(False)
-    # merge event, timed alone (burst peak)
-    torch.cuda.synchronize()
-    ops.profile_enable(True)
-    trainer.merge()
-    torch.cuda.synchronize()
-    mg_ms, mg_bytes, mg_n = ops.profile_read("merge")
-    ops.profile_enable(False)
+    # merge events, each timed alone by CUDA events inside the C ABI (burst peak).  After the first merge B = 0, so
+    # repeated merges leave W unchanged numerically while moving exactly the same bytes.
+    merge_ms = []
+    mg_bytes = 0.0
+    for _ in range(5):
+        torch.cuda.synchronize()
+        ops.profile_enable(True)
+        trainer.merge()
+        torch.cuda.synchronize()
+        ms_i, mg_bytes, mg_n = ops.profile_read("merge")
+        ops.profile_enable(False)
+        merge_ms.append(ms_i)
+    mg_ms = statistics.median(merge_ms)
+
+    # TT-Adam on a Llama-7B-shaped bf16 weight (BASELINE.json config 5), order 2: fused update + re-compression
+    tt_rows = {}
+    if rank == 0:
+        from tn_gradient.optimizer.ttadam import TTAdam
+        for r_tt in (8, 64):
+            Mt = Nt = 4096
+            p_tt = torch.nn.Parameter((torch.randn(Mt, Nt, device=device) * 0.02).to(torch.bfloat16))
+            p_tt.grad = (torch.randn(Mt, Nt, device=device) * 0.01).to(torch.bfloat16)
+            opt_tt = TTAdam([{"params": [p_tt], "ranks": [1, r_tt, 1]}], lr=1e-3)
+            for _ in range(3):
+                opt_tt.step()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                opt_tt.step()
+                a1.record()
+                torch.cuda.synchronize()
+                ts.append(a0.elapsed_time(a1))
+            t_ms = statistics.median(ts)
+            # algorithmic bytes: fused Adam g + p r/w = 6 B/elem; two decompositions 4*P*P each + cores
+            P_tt = 64 * 64
+            fused_bytes = Mt * Nt * 6
+            survey_bytes = fused_bytes + 2 * 4 * P_tt * P_tt + 2 * 4 * P_tt * P_tt + 4 * 4 * r_tt * 2 * P_tt
+            tt_rows[f"ttadam_4096x4096_order2_r{r_tt}"] = {
+                "bound": "hbm", "ms_per_step": t_ms, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                "achieved_fused_accounting": fused_bytes / t_ms / 1e6, "frac_fused_accounting": fused_bytes / t_ms / 1e6 / peaks["hbm_gbs"],
+                "achieved_survey_accounting": survey_bytes / t_ms / 1e6, "frac_survey_accounting": survey_bytes / t_ms / 1e6 / peaks["hbm_gbs"],
+                "note": "fused: bytes this implementation must move (g, p r/w); survey: + dense fp32 moments written and "
+                        "re-read by two decompositions (SURVEY.md 8d formula for an unfused pipeline)"}
+            del opt_tt, p_tt
+        torch.cuda.empty_cache()
 
     # dominant kernel: the fused SoW GEMM (forward y and backward dX are the same kernel template)
     gemm_ms = kern["gemm_fwd"]["ms_total"] + kern["gemm_dx"]["ms_total"]
@@ -235,7 +276,11 @@ def main():
     roofline = {
         "kernel": "sow_gemm_kernel<BN=256> (y = x.W + t.B and dX = dY.W^T + dt.A^T, tcgen05/TMEM/TMA)",
         "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+        "frac": achieved_tf / peak_tf if peak_tf else None,
+        # dram__bytes_read + dram__bytes_write of ONE launch from the committed ncu --set full capture
+        # (profiles/r01_gemm_v2_ncu_full_summary.csv, forward launch of the gate/up shape T=16384, 1024->2736, r=50;
+        # algorithmic bytes of that launch: x 33.6 + W 5.6 + y 89.7 + t,B 2.4 = 131 MB -- part of y is still dirty in L2)
+        "traffic": 82.16e6, "traffic_unit": "bytes/launch (ncu, gate/up forward at T=16384)",
         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
         "launches_timed": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
         "share_of_step": (gemm_ms / max(args.profile_steps, 1)) / step_ms,
@@ -243,8 +288,10 @@ def main():
     merge_gbs = mg_bytes / (mg_ms / 1e3) / 1e9 if mg_ms > 0 else 0.0
     extra_kernels = {
         "merge": {"bound": "hbm", "achieved": merge_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                  "frac": merge_gbs / peaks["hbm_gbs"], "ms": mg_ms, "algorithmic_bytes": mg_bytes, "launches": mg_n},
+                  "frac": merge_gbs / peaks["hbm_gbs"], "ms": mg_ms, "algorithmic_bytes": mg_bytes, "launches": mg_n,
+                  "events": len(merge_ms), "ms_all": merge_ms},
     }
+    extra_kernels.update(tt_rows)
     for k in ("gemm_skinny", "gemm_splitk", "adam"):
         d = kern[k]
         if d["ms_total"] > 0:
