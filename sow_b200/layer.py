@@ -262,7 +262,7 @@ def _merge_dense(mods: List[SoWLinear]) -> None:
         if W_new is not None:
             W_final = W_new if tgt_dtype == torch.bfloat16 else W_new.to(tgt_dtype)
             mod.acc_downweight = nn.Parameter(W_final, requires_grad=False)
-            mod.acc_upweight = nn.Parameter(torch.empty(0), requires_grad=False)
+            mod.acc_upweight = nn.Parameter(torch.empty(0, device=W_final.device), requires_grad=False)
         mod._w_shadow = None
         mod._w_shadow_key = None
 

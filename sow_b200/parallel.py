@@ -127,6 +127,8 @@ def assert_replicas_consistent(tensors: Iterable[torch.Tensor], what: str = "ten
     if not _dist_on():
         return
     for i, t in enumerate(tensors):
+        if t.numel() == 0:          # empty accumulation placeholders (acc_upweight) carry no data
+            continue
         ref = t.detach().clone()
         dist.broadcast(ref, src=0)
         diff = float((ref.float() - t.detach().float()).abs().max()) if t.numel() else 0.0
