@@ -169,6 +169,18 @@ int tt_adam2_fused(void* p, const void* g, const float* G1m, const float* G2m, c
                    const float* Qm, const float* Qv, float* Rm, float* Rv, int M, int N, int mm, int nn, double beta1,
                    double beta2, double eps, double step_size, double lr_wd, int first_step, int dtype, void* stream);
 
+/*
+ * The whole order-2 TT-Adam step in one call, with both rank-r products on the tensor cores (tcgen05, operands split
+ * into three bf16 pieces = fp32-accurate): tt_adam2_head -> sow_thin_qr -> operand split -> fused update + projection.
+ * Outputs the new cores: Q'{m,v} (Qm, Qv = the two halves of one (2, P, r) array) and R'{m,v} (r x P each).
+ * ws: tt_adam2_workspace_bytes(mm, nn) bytes, 256-byte aligned.  r <= 64.
+ */
+size_t tt_adam2_workspace_bytes(int mm, int nn);
+int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r,
+                  float* Qm, float* Qv, float* Rm, float* Rv, int M, int N, int mm, int nn, double beta1, double beta2,
+                  double eps, double step_size, double lr_wd, int first_step, int dtype, void* ws, size_t ws_bytes,
+                  void* stream);
+
 /* Same update on dense fp32 moments m, v of shape (M,N) (order > 2 path); v is clamped at 0 first (ttadam.py:84). */
 int tt_adam_dense(void* p, const void* g, float* m, float* v, int64_t numel, double beta1, double beta2, double eps,
                   double step_size, double lr_wd, int dtype, void* stream);

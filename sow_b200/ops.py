@@ -6,6 +6,7 @@ Every wrapper requires CUDA tensors and raises otherwise -- there is no CPU path
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 from typing import List, Optional, Sequence, Tuple
 
@@ -268,8 +269,9 @@ def tt_adam_fused2(p, g, cores_m, cores_v, mm, nn, beta1, beta2, eps, step_size,
 
 
 def tt_adam2_step(p, g, cores_m, cores_v, mm, nn, r, beta1, beta2, eps, step_size, lr_wd, first_step):
-    """Order-2 TT-Adam with the re-compression fused in (include/sow_b200.h: tt_adam2_head / tt_adam2_fused).
-    Returns the new cores ((Qm (P,r), Rm (r,P)), (Qv, Rv)); the dense moments never reach HBM."""
+    """Order-2 TT-Adam with the re-compression fused in; the dense moments never reach HBM.  ONE C-ABI call
+    (tt_adam2_step: head -> thin QR -> fused update + projection, on the tensor cores above rank 16).  Returns the new
+    cores ((Qm (P,r), Rm (r,P)), (Qv, Rv))."""
     _require_cuda(p, g)
     lib = _lib.load()
     M, N = p.shape
@@ -281,19 +283,14 @@ def tt_adam2_step(p, g, cores_m, cores_v, mm, nn, r, beta1, beta2, eps, step_siz
         G1m, G2m = cores_m
         G1v, G2v = cores_v
     g = g.contiguous()
-    dt = _dtype_code(p.dtype)
-    st = _stream_ptr(dev)
-    X = torch.empty((2, P, 64), dtype=torch.float32, device=dev)
-    rc = lib.tt_adam2_head(_p(g), _p(G1m), _p(G2m), _p(G1v), _p(G2v), r, _p(X[0]), _p(X[1]), M, N, mm, nn,
-                           float(beta1), float(beta2), 1 if first_step else 0, dt, st)
-    check(rc, "tt_adam2_head")
-    Q = thin_qr(X, r)                                   # (2, P, r): bases of the new moments
-    R = torch.zeros((2, r, P), dtype=torch.float32, device=dev)
-    rc = lib.tt_adam2_fused(_p(p), _p(g), _p(G1m), _p(G2m), _p(G1v), _p(G2v), r, _p(Q[0]), _p(Q[1]), _p(R[0]), _p(R[1]),
-                            M, N, mm, nn, float(beta1), float(beta2), float(eps), float(step_size), float(lr_wd),
-                            1 if first_step else 0, dt, st)
-    check(rc, "tt_adam2_fused")
-    launch_counter["kernels"] += 3
+    Q = torch.empty((2, P, r), dtype=torch.float32, device=dev)
+    R = torch.empty((2, r, P), dtype=torch.float32, device=dev)
+    ws = workspace(dev, lib.tt_adam2_workspace_bytes(mm, nn))
+    rc = lib.tt_adam2_step(_p(p), _p(g), _p(G1m), _p(G2m), _p(G1v), _p(G2v), r, _p(Q[0]), _p(Q[1]), _p(R[0]), _p(R[1]),
+                           M, N, mm, nn, float(beta1), float(beta2), float(eps), float(step_size), float(lr_wd),
+                           1 if first_step else 0, _dtype_code(p.dtype), _p(ws), ws.numel(), _stream_ptr(dev))
+    check(rc, "tt_adam2_step")
+    launch_counter["kernels"] += 8
     return (Q[0], R[0]), (Q[1], R[1])
 
 
