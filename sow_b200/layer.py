@@ -101,7 +101,10 @@ class _SoWLinearFn(torch.autograd.Function):
         return dx, None, dA, dB, dbias, None
 
 
+@torch.compiler.disable
 def sow_linear(x, W_c, A, B, bias, scale):
+    """Kernel-backed SoW linear.  Opaque to torch.compile (scripts/finetune.py:486-487 compiles the model): the C-ABI
+    calls are not traceable, so dynamo breaks the graph here and runs this call eagerly."""
     return _SoWLinearFn.apply(x, W_c, A, B, bias, scale)
 
 

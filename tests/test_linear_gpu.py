@@ -160,3 +160,22 @@ def test_unsupported_feature_size_fails_loudly():
     layer = SoWLinear(100, 5461 - 5461 % 2 + 1, bias=False, rank=4, init_method="normal", dtype=torch.bfloat16, device="cuda")
     with pytest.raises(SowB200Error, match="multiples of 8"):
         layer(torch.randn(4, 100, device="cuda", dtype=torch.bfloat16))
+
+
+def test_model_with_sow_layers_runs_under_torch_compile():
+    """scripts/finetune.py:486-487 wraps the model in torch.compile: the kernel call must stay opaque to dynamo (graph
+    break, eager execution of the C-ABI call) and give the same numbers as the uncompiled module."""
+    import torch.nn as nn
+    from tn_gradient.prepare import SoWConfig, prepare_sow
+    torch.manual_seed(0)
+    m = nn.Sequential(nn.Linear(256, 512), nn.GELU(), nn.Linear(512, 256))
+    m = prepare_sow(m, SoWConfig(target_modules=["0", "2"], rank=8, device="cuda", init_method="normal",
+                                 decompose="keep")).to("cuda", torch.bfloat16)
+    x = torch.randn(64, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y0 = m(x)
+    y0.float().pow(2).mean().backward()
+    g0 = x.grad.clone()
+    x.grad = None
+    y1 = torch.compile(m)(x)
+    y1.float().pow(2).mean().backward()
+    assert torch.equal(y0, y1) and torch.equal(g0, x.grad)
