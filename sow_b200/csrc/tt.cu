@@ -194,11 +194,13 @@ cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __res
 }
 
 // In place: lower triangle of G -> L; dinv[j] = 1 / L_jj (0 for a dependent column).  1024 threads, 4 entries each.
+// Right-looking Cholesky with the column scaling deferred: step j only needs the pivot d_j = A[j][j] and the unscaled
+// column j, A[i][k] -= A[i][j] A[k][j] / d_j, so there is ONE barrier per step; L = A . diag(d)^-1/2 at the end.
 __global__ void __launch_bounds__(1024)
 cq_chol_kernel(double* __restrict__ ws, int r) {
   __shared__ double A[kCqMaxR][kCqMaxR + 1];
   __shared__ double g0[kCqMaxR];
-  __shared__ double piv;       // L_jj of the current step (0 if dependent)
+  __shared__ double dfin[kCqMaxR];      // final pivots (0 for a dependent column)
   double* G = ws + blockIdx.x * (kCqMaxR * kCqMaxR + kCqMaxR);
   double* dinv = G + kCqMaxR * kCqMaxR;
   const int tid = threadIdx.x;
@@ -212,26 +214,15 @@ cq_chol_kernel(double* __restrict__ ws, int r) {
   if (tid < kCqMaxR) g0[tid] = A[tid][tid];
   __syncthreads();
   for (int j = 0; j < r; ++j) {
-    if (tid == 0) {
-      const double d = A[j][j];
-      const bool alive = (g0[j] > 1e-300) && (d > 1e-12 * g0[j]);
-      piv = alive ? sqrt(d) : 0.0;
-    }
-    __syncthreads();
-    const double ljj = piv;
-    const double inv = ljj > 0.0 ? 1.0 / ljj : 0.0;
-    if (tid > j && tid < r) A[tid][j] *= inv;            // column j of L (zero if dependent)
-    if (tid == 0) {
-      A[j][j] = ljj;
-      dinv[j] = inv;
-    }
-    __syncthreads();
-    if (i > j && i < r) {
-      const double lij = A[i][j];
+    const double d = A[j][j];                                       // final after step j-1 (broadcast read)
+    const bool alive = (g0[j] > 1e-300) && (d > 1e-12 * g0[j]);
+    if (tid == 0) dfin[j] = alive ? d : 0.0;
+    if (alive && i > j && i < r) {
+      const double f = A[i][j] / d;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int k = kb + 16 * c;
-        if (k > j && k <= i) A[i][k] -= lij * A[k][j];
+        if (k > j && k <= i) A[i][k] -= f * A[k][j];
       }
     }
     __syncthreads();
@@ -239,7 +230,15 @@ cq_chol_kernel(double* __restrict__ ws, int r) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int k = kb + 16 * c;
-    if (i < r && k <= i) G[i * kCqMaxR + k] = A[i][k];
+    if (i < r && k <= i) {
+      const double d = dfin[k];
+      const double s = d > 0.0 ? rsqrt(d) : 0.0;
+      G[i * kCqMaxR + k] = (k == i) ? (d > 0.0 ? sqrt(d) : 1.0) : A[i][k] * s;   // dependent column: L_jj = 1, rest 0
+    }
+  }
+  if (tid < r) {
+    const double d = dfin[tid];
+    dinv[tid] = d > 0.0 ? rsqrt(d) : 0.0;
   }
 }
 
@@ -273,10 +272,16 @@ cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __res
     for (int j = 0; j < kCqMaxR; ++j) {
       q[j] = 0.0;
       if (j < r) {
-        double acc = static_cast<double>(sx[tid][j]);
+        // four independent partial sums: the fp64 FMA chain is latency-bound with one row per thread
+        double a0 = static_cast<double>(sx[tid][j]), a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int k = 0; k < j; ++k) acc = fma(-q[k], sL[k][j], acc);
-        q[j] = acc * sdinv[j];
+        for (int k = 0; k < j; ++k) {
+          if ((k & 3) == 0) a0 = fma(-q[k], sL[k][j], a0);
+          else if ((k & 3) == 1) a1 = fma(-q[k], sL[k][j], a1);
+          else if ((k & 3) == 2) a2 = fma(-q[k], sL[k][j], a2);
+          else a3 = fma(-q[k], sL[k][j], a3);
+        }
+        q[j] = ((a0 + a1) + (a2 + a3)) * sdinv[j];
       }
     }
 #pragma unroll
