@@ -185,7 +185,8 @@ def test_tt_decomposition_at_llama7b_shapes_vs_projection_oracle(M, N, r):
     assert float((G1.T @ G1 - torch.eye(r, device="cuda")).abs().max()) < 1e-5
 
 
-@pytest.mark.parametrize("M,N,r,dtype", [(4096, 4096, 64, torch.bfloat16), (4096, 11008, 8, torch.float32)])
+@pytest.mark.parametrize("M,N,r,dtype", [(4096, 4096, 64, torch.bfloat16), (4096, 11008, 8, torch.float32),
+                                         (4096, 4096, 32, torch.float32), (1024, 4096, 48, torch.float32)])
 def test_ttadam_fused_step_at_llama7b_shapes(M, N, r, dtype):
     """Config 5: two TTAdam steps (ttadam.py:61-115).  Step 1 starts from zero moments, so the parameter update is the
     dense Adam update; step 2 must use the reconstruction of the compressed moments, and the new compressed moments
