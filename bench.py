@@ -312,6 +312,19 @@ def main():
                         "sample": f"3 steps of 2x{S} tokens ({args.model} SoW r={args.rank}, fp32, merge in warm-up), "
                                   f"{res['sec_per_step']:.2f} s/step"}
 
+    # ---- the reference's own eager formulation on the SAME GPU (oracle port in bf16 on cuda; rank 0, N=1 only):
+    # the practical bar of BASELINE.md section 5, reported beside the CPU baseline, not part of `value`
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del trainer
+        torch.cuda.empty_cache()
+        from oracle.cpu_trainer import time_cpu_training
+        res = time_cpu_training(args.model, args.rank, batch=B, seq_len=S, steps=5, warmup=3, device=str(device),
+                                dtype=torch.bfloat16)
+        gpu_eager = {"value": res["tokens_per_s"], "unit": "tokens/s", "kind": "port (eager torch ops of the reference, bf16, "
+                     "torch.optim.AdamW) on the same B200", "sample": f"5 steps of {B}x{S} tokens, {res['sec_per_step'] * 1e3:.1f} ms/step",
+                     "speedup_of_this_build": value / res["tokens_per_s"]}
+
     if rank == 0:
         shp = LLAMA_SHAPES[args.model]
         line = {
@@ -331,6 +344,7 @@ def main():
             "roofline": roofline,
             "kernels": extra_kernels,
             "cpu_baseline": cpu_baseline,
+            "gpu_eager_baseline": gpu_eager,
             "clocks": clocks,
             "loss": final_loss,
         }

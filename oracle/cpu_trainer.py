@@ -67,13 +67,19 @@ def build_port_model(name: str, rank: int, seq_len: int = 256, seed: int = 42) -
 
 
 def time_cpu_training(model_name: str = "llama_350m", rank: int = 50, batch: int = 2, seq_len: int = 256,
-                      steps: int = 2, warmup: int = 1, threads: int = 0) -> dict:
-    """fp32 CPU training steps in the loop order of scripts/simple_train.py:611-650 (one merge during warm-up so
-    the timed steps are the steady state with a dense W).  Returns tokens/s and per-step seconds."""
+                      steps: int = 2, warmup: int = 1, threads: int = 0, device: str = "cpu",
+                      dtype: torch.dtype = torch.float32) -> dict:
+    """Training steps of the port in the loop order of scripts/simple_train.py:611-650 (one merge during warm-up so
+    the timed steps are the steady state with a dense W).  Returns tokens/s and per-step seconds.
+
+    device="cpu", fp32: the reference's CPU path on the host cores (the reported baseline).  device="cuda", bf16: the
+    same eager formulation (three cuBLAS mm + mul + add per layer, stack/sum/add merge, torch.optim.AdamW) on the GPU --
+    what the reference itself would run there; an extra baseline leg of bench.py, never part of the product."""
     import os
     n = threads or os.cpu_count() or 1
-    torch.set_num_threads(n)
-    model = build_port_model(model_name, rank, seq_len)
+    if device == "cpu":
+        torch.set_num_threads(n)
+    model = build_port_model(model_name, rank, seq_len).to(device=device, dtype=dtype)
     sow: List[PortSoWLinear] = [m for m in model.modules() if isinstance(m, PortSoWLinear)]
     factors = [p for m in sow for p in (m.A, m.B)]
     ids = {id(p) for p in factors}
@@ -84,7 +90,9 @@ def time_cpu_training(model_name: str = "llama_350m", rank: int = 50, batch: int
     times = []
     merge_s = 0.0
     for step in range(warmup + steps):
-        ids_ = torch.randint(1, 32000, (batch, seq_len), generator=g)
+        ids_ = torch.randint(1, 32000, (batch, seq_len), generator=g).to(device)
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         loss = model(input_ids=ids_, labels=ids_).loss
         loss.backward()
@@ -100,6 +108,8 @@ def time_cpu_training(model_name: str = "llama_350m", rank: int = 50, batch: int
             merge_s = time.perf_counter() - tm
         opt.step()
         opt.zero_grad()
+        if device != "cpu":
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if step >= warmup:
             times.append(dt)
