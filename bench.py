@@ -220,13 +220,16 @@ def main():
         tms, work, n = ops.profile_read(k)
         kern[k] = {"ms_total": tms, "work": work, "launches": n}
     ops.profile_enable(False)
-    # merge events, each timed alone by CUDA events inside the C ABI (burst peak).  After the first merge B = 0, so
-    # repeated merges leave W unchanged numerically while moving exactly the same bytes.
+    # merge events, each timed by CUDA events inside the C ABI around the single grouped launch.  As in training
+    # (simple_train.py:618-626) the merge is issued right behind a backward pass, with no host synchronisation in
+    # between, so the GPU is at its working clocks.  After the first merge B = 0, so repeated merges leave W unchanged
+    # numerically while moving exactly the same bytes.
     merge_ms = []
     mg_bytes = 0.0
-    for _ in range(5):
+    for i in range(5):
         torch.cuda.synchronize()
         ops.profile_enable(True)
+        trainer.step(dev_batches[i % n_batches])
         trainer.merge()
         torch.cuda.synchronize()
         ms_i, mg_bytes, mg_n = ops.profile_read("merge")
