@@ -74,6 +74,11 @@ class _SoWLinearFn(torch.autograd.Function):
         out_dtype = x.dtype
         fin = A.shape[0]
         lead = x.shape[:-1]
+        if x.numel() == 0:                      # empty batch: nothing to launch (the reference returns an empty tensor too)
+            ctx.empty = True
+            ctx.meta = (x.dtype, A, B, bias, lead, fin)
+            return x.new_zeros(*lead, B.shape[1])
+        ctx.empty = False
         x2 = _bf16c(x.reshape(-1, fin))
         A_c, B_c, bias_c = _bf16c(A), _bf16c(B), _bf16c(bias)
         y, t = ops.linear_fwd(x2, W_c, A_c, B_c, bias_c, scale)
@@ -85,6 +90,12 @@ class _SoWLinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        if ctx.empty:
+            _, A, B, bias, lead, fin = ctx.meta
+            need_x, _, need_A, need_B, need_bias, _ = ctx.needs_input_grad
+            return (dy.new_zeros(*lead, fin) if need_x else None, None, torch.zeros_like(A) if need_A else None,
+                    torch.zeros_like(B) if need_B else None,
+                    torch.zeros_like(bias) if (need_bias and bias is not None) else None, None)
         x2, t, W_c, A_c, B_c = ctx.saved_tensors
         out_dtype, a_dt, b_dt, bias_dt, lead, fin = ctx.meta
         need_x, _, need_A, need_B, need_bias, _ = ctx.needs_input_grad

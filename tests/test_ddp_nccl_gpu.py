@@ -64,6 +64,55 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+def _worker_stock_ddp(rank, world, port, ret):
+    """SoWLinear under the reference's own wrapper, torch DistributedDataParallel (scripts/simple_train.py:566-572)."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import torch.nn as nn
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from tn_gradient.prepare import SoWConfig, accumulate, prepare_sow
+        torch.manual_seed(0)
+        model = nn.Sequential(nn.Linear(256, 512, bias=False), nn.GELU(), nn.Linear(512, 256, bias=False))
+        model = prepare_sow(model, SoWConfig(target_modules=["0", "2"], rank=8, device=str(dev), init_method="normal",
+                                             decompose="keep")).to(dev, torch.bfloat16)
+        ddp = DDP(model, device_ids=[rank], broadcast_buffers=False)
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-2)
+        g = torch.Generator().manual_seed(5)
+        data = torch.randn(3, world * 16, 256, generator=g)
+        for step in range(3):
+            x = data[step, rank * 16:(rank + 1) * 16].to(dev, torch.bfloat16)
+            ddp(x).float().pow(2).mean().backward()
+            if step == 1:
+                accumulate(model)                      # replica-local merge; A re-init broadcast from rank 0
+            opt.step()
+            opt.zero_grad()
+        flat = torch.cat([p.detach().float().flatten() for p in model.parameters() if p.numel()])
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        ret[rank] = float((flat - ref).abs().max())
+    except Exception as e:  # pragma: no cover
+        import traceback
+        ret[rank] = "".join(traceback.format_exception(type(e), e, e.__traceback__))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_sow_layers_under_stock_ddp_stay_in_sync():
+    import torch.multiprocessing as mp
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_stock_ddp, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in range(2):
+        assert ret.get(r) == 0.0, f"rank {r}: {ret.get(r)}"
+
+
 def test_two_rank_training_with_merge_keeps_replicas_consistent():
     import torch.multiprocessing as mp
     mgr = mp.get_context("spawn").Manager()

@@ -179,3 +179,14 @@ def test_model_with_sow_layers_runs_under_torch_compile():
     y1 = torch.compile(m)(x)
     y1.float().pow(2).mean().backward()
     assert torch.equal(y0, y1) and torch.equal(g0, x.grad)
+
+
+def test_empty_batch_returns_empty_output_and_zero_grads():
+    from tn_gradient.layer.sow import SoWLinear
+    layer = SoWLinear(64, 128, bias=True, rank=8, init_method="normal", dtype=torch.bfloat16, device="cuda")
+    x = torch.empty(0, 7, 64, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = layer(x)
+    assert y.shape == (0, 7, 128)
+    y.sum().backward()
+    assert x.grad.shape == x.shape
+    assert float(layer.downscale_weights[0].grad.abs().max()) == 0.0 and float(layer.bias.grad.abs().max()) == 0.0
