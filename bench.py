@@ -33,6 +33,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=128,
                     help="sequences per GPU per step (128 = the reference's documented pre-training recipe, readme.md:5-26)")
     ap.add_argument("--seq", type=int, default=256)
+    ap.add_argument("--mode", default="pretrain", choices=["pretrain", "keep"],
+                    help="pretrain: empty accumulation, everything trains (config 2); keep: fine-tune of a dense model, "
+                         "frozen base, only the factors train (configs 3-4)")
+    ap.add_argument("--act-ckpt", action="store_true", help="activation checkpointing (config 4: Llama-7B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-optimizer", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
@@ -151,7 +155,9 @@ def main():
     peaks = load_peaks()
 
     cfg = TrainConfig(model=args.model, rank=args.rank, seq_len=args.seq, batch_size=args.batch,
-                      fused_optimizer=not args.no_fused_optimizer)
+                      fused_optimizer=not args.no_fused_optimizer, decompose="keep" if args.mode == "keep" else None,
+                      freeze_base=args.mode == "keep", activation_checkpointing=args.act_ckpt,
+                      scale=1.0 if args.mode == "pretrain" else 0.125)
     trainer = SoWTrainer(cfg, device)
     B, S = args.batch, args.seq
     n_batches = 8
@@ -336,7 +342,8 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {
                 "workload": f"{args.model} (h={shp['hidden_size']}, ff={shp['intermediate_size']}, L={shp['num_hidden_layers']}) "
-                            f"SoW rank {args.rank} bf16 pre-training, steady state after 1 merge (dense W), "
+                            f"SoW rank {args.rank} bf16 " + ("pre-training" if args.mode == "pretrain" else "fine-tuning (mode keep, frozen base"
+                            + (", activation checkpointing" if args.act_ckpt else "") + ")") + ", steady state after 1 merge (dense W), "
                             f"fwd+bwd+grad-avg+fused AdamW per step",
                 "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "tokens_per_step": tokens_per_step,
                 "parallelism": f"dp{world}", "l2": "working set per step (>1 GB weights+activations) exceeds the 126 MB L2; no flush needed",

@@ -30,15 +30,24 @@ LLAMA_SHAPES: Dict[str, Dict[str, int]] = {
 LLAMA_TARGETS = ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]   # simple_train.py:318
 
 
-def build_llama(name: str, seq_len: int = 256, vocab_size: int = 32000, seed: int = 42) -> nn.Module:
-    """Random-init HF Llama of the named reference config (AutoModelForCausalLM.from_config, simple_train.py:313-314)."""
+def build_llama(name: str, seq_len: int = 256, vocab_size: int = 32000, seed: int = 42,
+                dtype: Optional[torch.dtype] = None) -> nn.Module:
+    """Random-init HF Llama of the named reference config (AutoModelForCausalLM.from_config, simple_train.py:313-314).
+    ``dtype`` builds the parameters directly in that dtype (halves the host memory of the 7B config)."""
     from transformers import LlamaConfig, LlamaForCausalLM
     shp = LLAMA_SHAPES[name]
     cfg = LlamaConfig(vocab_size=vocab_size, max_position_embeddings=max(1024, seq_len), rms_norm_eps=1e-6,
                       hidden_act="silu", initializer_range=0.02, bos_token_id=0, eos_token_id=1, use_cache=False,
                       tie_word_embeddings=False, **shp)
     torch.manual_seed(seed)
-    return LlamaForCausalLM(cfg)
+    if dtype is None:
+        return LlamaForCausalLM(cfg)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        return LlamaForCausalLM(cfg)
+    finally:
+        torch.set_default_dtype(prev)
 
 
 def reset_optimizer(optimizer: torch.optim.Optimizer, group_id: int) -> None:
@@ -76,6 +85,8 @@ class TrainConfig:
     activation_checkpointing: bool = False
     fused_optimizer: bool = True
     overlap_grad_sync: bool = True
+    decompose: Optional[str] = None      # None: pre-training (empty accumulation); "keep": fine-tuning of a dense model
+    freeze_base: bool = False            # fine-tuning: only the SoW factors train (run_glue.py:515-516,547-553)
 
 
 class SoWTrainer:
@@ -84,9 +95,10 @@ class SoWTrainer:
     def __init__(self, cfg: TrainConfig, device: torch.device):
         self.cfg = cfg
         self.device = device
-        model = build_llama(cfg.model, cfg.seq_len, seed=cfg.seed)
+        big = LLAMA_SHAPES[cfg.model]["hidden_size"] >= 2048
+        model = build_llama(cfg.model, cfg.seq_len, seed=cfg.seed, dtype=cfg.dtype if big else None)
         sow_cfg = SoWConfig(target_modules=LLAMA_TARGETS, rank=cfg.rank, init_method=cfg.init_method, scale=cfg.scale,
-                            decompose=None, device=str(device))
+                            decompose=cfg.decompose, device=str(device))
         model = prepare_sow(model, sow_cfg)                                        # simple_train.py:318-331
         special, ids = [], set()
         for m in sow_modules(model):                                                # simple_train.py:389-405
@@ -95,12 +107,21 @@ class SoWTrainer:
                 ids.add(id(p))
         if cfg.activation_checkpointing:
             model.gradient_checkpointing_enable()
+            if cfg.freeze_base and hasattr(model, "enable_input_require_grads"):
+                model.enable_input_require_grads()       # frozen embeddings: keep the checkpointed segments differentiable
         model = model.to(device=device, dtype=cfg.dtype)                           # simple_train.py:425-428
+        if cfg.freeze_base:
+            for p in model.parameters():
+                if id(p) not in ids:
+                    p.requires_grad_(False)
         self.trainable = [p for p in model.parameters() if p.requires_grad and id(p) not in ids]
         self.special = special
         self.model = model
-        groups = [{"params": self.trainable, "lr": cfg.lr, "weight_decay": cfg.weight_decay},
-                  {"params": self.special, "lr": cfg.sow_lr, "weight_decay": cfg.weight_decay}]
+        groups = []
+        if self.trainable:
+            groups.append({"params": self.trainable, "lr": cfg.lr, "weight_decay": cfg.weight_decay})
+        self.sow_group_id = len(groups)
+        groups.append({"params": self.special, "lr": cfg.sow_lr, "weight_decay": cfg.weight_decay})
         self.optimizer = FusedAdamW(groups) if cfg.fused_optimizer else torch.optim.AdamW(groups)   # :502-506
         broadcast_parameters(model)                                                # DDP ctor semantics (:566-572)
         self.grad_sync = FlatGradSync(self.trainable + self.special, overlap=cfg.overlap_grad_sync)
@@ -132,7 +153,7 @@ class SoWTrainer:
 
     def merge(self) -> None:
         accumulate(self.model)
-        reset_optimizer(self.optimizer, group_id=1)
+        reset_optimizer(self.optimizer, group_id=self.sow_group_id)
         self.merges += 1
 
     def tokens_per_step(self) -> int:
