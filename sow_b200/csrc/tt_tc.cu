@@ -220,9 +220,13 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
   auto stamp = [&](int t, int k) {
     if (prm.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && t - t_begin < 64) prm.dbg[(t - t_begin) * 8 + k] = clock64();
   };
-  for (int t = t_begin; t < t_end; ++t) {
+  // CTAs of different strips read the same core / Q' rows: start each strip at a different row tile so that they do not
+  // hit the same L2 lines at the same time (the projection sum is order-independent)
+  const int n_local = t_end - t_begin;
+  for (int it = 0; it < n_local; ++it) {
+    const int t = t_begin + (it + static_cast<int>(blockIdx.x)) % n_local;
     const int a0 = t * kTcTile;
-    stamp(t, 0);
+    stamp(t_begin + it, 0);
     const int ga = a0 + rloc;
     const int i1 = ga / nn, o1 = ga - i1 * nn;
     const int64_t rowbase = static_cast<int64_t>(i1) * mm * N + static_cast<int64_t>(o1) * nn;
@@ -271,28 +275,28 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
     }
     // ---------------- 1. loads + reconstruction UMMAs (one thread) ----------------
     if (tid == 0) {
-      mbar_expect_tx(bar_q, kTcQBytes);
-#pragma unroll
-      for (int pc = 0; pc < 3; ++pc) {
-        tma_load_2d(sQ + pc * 16384, &tmQm, bar_q, 0, pc * prm.P_pad + a0);
-        tma_load_2d(sQ + 49152 + pc * 16384, &tmQv, bar_q, 0, pc * prm.P_pad + a0);
-      }
       if (!prm.first_step) {
-#pragma unroll 1
+        // both moments' core pieces at once: m into the operand region, v into the (still idle) Q' region
+        mbar_expect_tx(bar_ld, 2 * kTcOpBytes);
+#pragma unroll
         for (int mom = 0; mom < 2; ++mom) {
           const CUtensorMap* m1 = mom ? &tmG1v : &tmG1m;
           const CUtensorMap* m2 = mom ? &tmG2v : &tmG2m;
-          mbar_expect_tx(bar_ld, kTcOpBytes);
+          uint8_t* base = mom ? sQ : sOp;
 #pragma unroll
           for (int pc = 0; pc < 3; ++pc) {
-            tma_load_2d(sOp + pc * 16384, m1, bar_ld, 0, pc * prm.P_pad + a0);
-            tma_load_2d(sOp + 49152 + pc * 16384, m2, bar_ld, b0, pc * 64);
-            tma_load_2d(sOp + 49152 + pc * 16384 + 8192, m2, bar_ld, b0 + 64, pc * 64);
+            tma_load_2d(base + pc * 16384, m1, bar_ld, 0, pc * prm.P_pad + a0);
+            tma_load_2d(base + 49152 + pc * 16384, m2, bar_ld, b0, pc * 64);
+            tma_load_2d(base + 49152 + pc * 16384 + 8192, m2, bar_ld, b0 + 64, pc * 64);
           }
-          mbar_wait(bar_ld, ph_ld);
-          ph_ld ^= 1;
-          tc_fence_after();
+        }
+        mbar_wait(bar_ld, ph_ld);
+        ph_ld ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int mom = 0; mom < 2; ++mom) {
           const uint32_t tS = mom ? tS_v : tS_m;
+          const uint32_t ob = mom ? sQ_u : sOp_u;
           bool first = true;
 #pragma unroll
           for (int i = 0; i < 3; ++i)
@@ -300,22 +304,29 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
             for (int j = 0; j < 3; ++j) {
               if (i + j > 2) continue;
               for (int k = 0; k < ksteps1; ++k) {
-                const uint64_t ad = make_smem_desc(sOp_u + i * 16384 + k * 32, 16, 1024);
-                const uint64_t bd = make_smem_desc(sOp_u + 49152 + j * 16384 + k * 2048, 8192, 1024);
+                const uint64_t ad = make_smem_desc(ob + i * 16384 + k * 32, 16, 1024);
+                const uint64_t bd = make_smem_desc(ob + 49152 + j * 16384 + k * 2048, 8192, 1024);
                 umma_bf16(tS, ad, bd, idesc1, first ? 0u : 1u);
                 first = false;
               }
             }
-          umma_commit(bar_mma);
-          mbar_wait(bar_mma, ph_mma);     // the operand tiles are overwritten next (other moment / m' pieces)
-          ph_mma ^= 1;
         }
+        umma_commit(bar_mma);
+        mbar_wait(bar_mma, ph_mma);     // both operand regions are overwritten next (m' pieces / Q' pieces)
+        ph_mma ^= 1;
+      }
+      // the Q' pieces of this row tile land while the Adam epilogue runs
+      mbar_expect_tx(bar_q, kTcQBytes);
+#pragma unroll
+      for (int pc = 0; pc < 3; ++pc) {
+        tma_load_2d(sQ + pc * 16384, &tmQm, bar_q, 0, pc * prm.P_pad + a0);
+        tma_load_2d(sQ + 49152 + pc * 16384, &tmQv, bar_q, 0, pc * prm.P_pad + a0);
       }
     }
     __syncthreads();
     __syncwarp();                 // lane 0 of warp 0 diverged above; tcgen05.ld is .sync.aligned
     tc_fence_after();
-    stamp(t, 1);
+    stamp(t_begin + it, 1);
 
     // ---------------- 2./4. epilogues: pass 0 = Adam + m' pieces, pass 1 = v' pieces ----------------
 #pragma unroll 1
@@ -429,7 +440,7 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
       fence_proxy_async_smem();     // generic-proxy writes of the operand tiles -> visible to the tensor core
       tc_fence_before();
       __syncthreads();
-      stamp(t, 2 + 2 * pass);
+      stamp(t_begin + it, 2 + 2 * pass);
       // ---------------- 3./5. projection UMMAs ----------------
       if (tid == 0) {
         if (pass == 0) {
@@ -439,7 +450,7 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
         tc_fence_after();
         const uint32_t tD = pass ? tD_v : tD_m;
         const uint32_t qb = sQ_u + (pass ? 49152 : 0);
-        bool first = (t == t_begin);
+        bool first = (it == 0);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -460,7 +471,7 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
       __syncthreads();
       __syncwarp();
       tc_fence_after();
-      stamp(t, 3 + 2 * pass);
+      stamp(t_begin + it, 3 + 2 * pass);
     }
   }
 
