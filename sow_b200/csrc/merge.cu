@@ -25,8 +25,11 @@
 //   warps 14-17: store group.  Coalesced 16-byte global stores of the finished tile (2 rows x 256 B per warp
 //                instruction), clipped at the matrix edge; frees the slot.
 //
-// 4 W slots of 32 KB keep >= 2 tile loads in flight per SM while one tile is in the epilogue and one is being
-// stored.
+// 3 W slots of 32 KB keep a tile load in flight per SM while one tile is in the epilogue and one is being stored
+// (4 slots measured no faster: the memory system, not the slot count, binds).  The scalar fields of every table
+// entry are staged in shared memory at kernel start and the next matrix's tensor maps are prefetched one matrix
+// ahead, because under HBM saturation a dependent global load costs microseconds.
+// Debug aid: sow_merge_debug_timeline() makes CTA 0 record clock64 stamps per tile (tools/merge_timeline.py).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -45,7 +48,7 @@ constexpr int kMgSlotBytes = kMgWBytes;
 constexpr int kMgStrip = 4;                         // column tiles per strip (B tiles resident in smem)
 constexpr int kMgAcc = 4;                           // TMEM accumulator stages
 constexpr int kMgMaxEntries = 384;                  // per launch (longer tables are split by the host)
-constexpr int kMgNumBars = 3 * kMgSlots + 2 * kMgAcc + 4 + 2 * kMgStrip;   // + one 8-byte cell for the TMEM address
+constexpr int kMgNumBars = 3 * kMgSlots + 2 * kMgAcc + 3 + 2 * kMgStrip;   // + one 8-byte cell for the TMEM address
 constexpr int kMgBarBytes = 320;
 static_assert((kMgNumBars + 1) * 8 <= kMgBarBytes, "barrier block overflows into the entry table");
 constexpr int kMgSmemTotal =
@@ -168,10 +171,9 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
   uint64_t* tfull_bar = bars + 3 * kMgSlots;          // [kMgAcc] 1 (umma commit)
   uint64_t* tempty_bar = tfull_bar + kMgAcc;          // [kMgAcc] 256
   uint64_t* astage_full = tempty_bar + kMgAcc;        // 1 + tx
-  uint64_t* astage_empty = astage_full + 1;           // 128
-  uint64_t* a_full = astage_full + 2;                 // 128
-  uint64_t* a_empty = astage_full + 3;                // 1 (umma commit)
-  uint64_t* b_full = astage_full + 4;                 // [kMgStrip] 1 + tx
+  uint64_t* a_full = astage_full + 1;                 // 128
+  uint64_t* a_empty = astage_full + 2;                // 1 (umma commit)
+  uint64_t* b_full = astage_full + 3;                 // [kMgStrip] 1 + tx
   uint64_t* b_empty = b_full + kMgStrip;              // [kMgStrip] 1 (umma commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMgStrip);
   MergeInfo* info = reinterpret_cast<MergeInfo*>(reinterpret_cast<uint8_t*>(bars) + kMgBarBytes);
@@ -209,7 +211,6 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
       mbar_init(&b_empty[i], 1);
     }
     mbar_init(astage_full, 1);
-    mbar_init(astage_empty, kMgRepackThreads);
     mbar_init(a_full, kMgRepackThreads);
     mbar_init(a_empty, 1);
     fence_mbar_init();
