@@ -231,3 +231,29 @@ def test_ttadam_fused_step_at_llama7b_shapes(M, N, r, dtype):
     want2, _, _ = dense_update(p1, g2, m1_tt, v1_tt, 2)
     assert _rel(p.detach().float() - p1.float(), want2 - p1.float()) < tol
     assert st is opt.state[p] and opt.state[p]["step"] == 2
+
+
+def test_decompose_qr_surgery_preserves_the_layer_function():
+    """prepare_sow(decompose='qr') (prepare.py:122-147): W^T = Q R is split into a frozen major part Q[:, :-r] R[:-r, :] and the
+    trainable minor factors Q[:, -r:], R[-r:, :]; with scale = 1 the SoW layer reproduces the dense layer it replaced."""
+    from tn_gradient.layer.sow import SoWLinear
+    from tn_gradient.prepare import SoWConfig, prepare_sow
+    torch.manual_seed(4)
+    dense = nn.Sequential(nn.Linear(512, 1376, bias=True), nn.Linear(1376, 512, bias=False)).to("cuda")
+    x = torch.randn(256, 512, device="cuda")
+    with torch.no_grad():
+        want = [dense[0](x), dense[1](torch.tanh(dense[0](x)))]
+    model = prepare_sow(dense, SoWConfig(target_modules=["0", "1"], rank=8, scale=1.0, device="cuda", decompose="qr"))
+    assert all(isinstance(m, SoWLinear) for m in model)
+    for m in model:
+        assert m.acc_downweight.shape == (m.in_features, m.out_features) and not m.acc_downweight.requires_grad
+        assert m.downscale_weights[0].shape == (m.in_features, 8) and m.upscale_weights[0].shape == (8, m.out_features)
+        A = m.downscale_weights[0].float()
+        assert float((A.T @ A - torch.eye(8, device="cuda")).abs().max()) < 1e-4        # columns of Q
+    with torch.no_grad():
+        got = [model[0](x), model[1](torch.tanh(model[0](x)))]
+    for g, w in zip(got, want):
+        assert _rel(g, w) < 1e-2                                                        # bf16 compute policy on fp32 modules
+    # the minor factors train, the major part does not
+    model[1](torch.tanh(model[0](x))).pow(2).mean().backward()
+    assert model[0].downscale_weights[0].grad is not None and model[0].acc_downweight.grad is None
