@@ -91,6 +91,50 @@ struct MapKeyHash {
   }
 };
 
+// A thread that has issued no CUDA call yet (autograd's per-device worker when the first backward node is ours) has no
+// current driver context, and cuTensorMapEncodeTiled then fails with CUDA_ERROR_INVALID_CONTEXT.  Bind the primary
+// context of the device that owns `ptr` -- derived from the pointer, not from the runtime's per-thread default (device 0),
+// so that rank k of a multi-GPU job never touches another device.
+typedef CUresult (*CtxGetCurrentFn)(CUcontext*);
+typedef CUresult (*CtxSetCurrentFn)(CUcontext);
+typedef CUresult (*PtrGetAttrFn)(void*, CUpointer_attribute, CUdeviceptr);
+typedef CUresult (*PrimaryRetainFn)(CUcontext*, CUdevice);
+typedef CUresult (*DeviceGetFn)(CUdevice*, int);
+
+int ensure_context_for(const void* ptr) {
+  static CtxGetCurrentFn get_cur = nullptr;
+  static CtxSetCurrentFn set_cur = nullptr;
+  static PtrGetAttrFn ptr_attr = nullptr;
+  static PrimaryRetainFn retain = nullptr;
+  static DeviceGetFn dev_get = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    auto fetch = [](const char* name) -> void* {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+      return p;
+    };
+    get_cur = reinterpret_cast<CtxGetCurrentFn>(fetch("cuCtxGetCurrent"));
+    set_cur = reinterpret_cast<CtxSetCurrentFn>(fetch("cuCtxSetCurrent"));
+    ptr_attr = reinterpret_cast<PtrGetAttrFn>(fetch("cuPointerGetAttribute"));
+    retain = reinterpret_cast<PrimaryRetainFn>(fetch("cuDevicePrimaryCtxRetain"));
+    dev_get = reinterpret_cast<DeviceGetFn>(fetch("cuDeviceGet"));
+  });
+  if (!get_cur || !set_cur || !ptr_attr || !retain || !dev_get || ptr == nullptr) return SOWB_OK;   // best effort
+  CUcontext cur = nullptr;
+  if (get_cur(&cur) == CUDA_SUCCESS && cur != nullptr) return SOWB_OK;
+  int ordinal = -1;
+  if (ptr_attr(&ordinal, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS || ordinal < 0)
+    return SOWB_OK;
+  CUdevice dev;
+  CUcontext primary = nullptr;
+  if (dev_get(&dev, ordinal) != CUDA_SUCCESS || retain(&primary, dev) != CUDA_SUCCESS || primary == nullptr)
+    return set_error(SOWB_ECUDA, "could not retain the primary context of device %d", ordinal);
+  if (set_cur(primary) != CUDA_SUCCESS) return set_error(SOWB_ECUDA, "could not bind the primary context of device %d", ordinal);
+  return SOWB_OK;
+}
+
 int make_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                        uint32_t box_inner, uint32_t box_outer, int elem_bytes) {
   if (base == nullptr) return set_error(SOWB_EINVAL, "tensor map: null base pointer");
@@ -115,6 +159,10 @@ int make_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint6
   }
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error(SOWB_ECUDA, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  {
+    const int rc = ensure_context_for(base);
+    if (rc) return rc;
+  }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};

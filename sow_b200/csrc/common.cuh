@@ -32,6 +32,9 @@ int num_sms();
 // 0 if the current device is sm_100, else an error code (message set).
 int require_sm100();
 
+// Bind the primary context of the device owning `ptr` to the calling thread if the thread has none (see common.cu).
+int ensure_context_for(const void* ptr);
+
 // 2-D row-major tensor map with 128B swizzle.  `inner` is the contiguous dimension (elements), `outer` the row
 // count, `pitch_bytes` the row pitch; box = (box_inner x box_outer) elements.  elem_bytes: 2 (bf16) or 4 (fp32).
 int make_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,

@@ -30,7 +30,8 @@ constexpr int kStageCBytes = kBM * kStoreBoxCols * 2;              // 16 KB per 
 
 enum EpiMode : int {
   EPI_BF16_TMA = 0,    // D -> bf16, via smem staging + TMA store (clips M/N tails)
-  EPI_F32_ATOMIC = 1,  // D -> fp32 red.global.add into out_f32[row*ldc + col]  (split-K partial sums)
+  EPI_F32_ATOMIC = 1,  // D -> fp32 PARTIAL of split s stored at out_f32[s*split_stride + row*ldc + col]; the caller sums the
+                       // splits in a fixed order (bit-reproducible, unlike red.global.add; no zero-fill needed)
 };
 
 struct GemmParams {
@@ -42,6 +43,7 @@ struct GemmParams {
   float alpha;
   const __nv_bfloat16* bias;  // nullable, length N (EPI_BF16_TMA only)
   float* out_f32;             // EPI_F32_ATOMIC only
+  int64_t split_stride;       // EPI_F32_ATOMIC only: elements between the partial outputs of consecutive splits
   int ldc;
 };
 
@@ -256,6 +258,8 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       } else {
         const int row = m0 + row_in_tile;
+        const int split = w % p.splits;
+        float* part = p.out_f32 + static_cast<int64_t>(split) * p.split_stride;
 #pragma unroll 1
         for (int c32 = 0; c32 < BN / 32; ++c32) {
           if (n0 + c32 * 32 >= p.N) break;
@@ -263,10 +267,17 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld32(taddr + c32 * 32, v);
           tmem_ld_wait();
           if (row < p.M) {
-            float* dst = p.out_f32 + static_cast<size_t>(row) * p.ldc + n0 + c32 * 32;
+            float* dst = part + static_cast<int64_t>(row) * p.ldc + n0 + c32 * 32;
+            if (n0 + c32 * 32 + 32 <= p.N && (p.ldc & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n0 + c32 * 32 + j < p.N) atomicAdd(dst + j, p.alpha * __uint_as_float(v[j]));
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(dst + 4 * j) =
+                    make_float4(p.alpha * __uint_as_float(v[4 * j]), p.alpha * __uint_as_float(v[4 * j + 1]),
+                                p.alpha * __uint_as_float(v[4 * j + 2]), p.alpha * __uint_as_float(v[4 * j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c32 * 32 + j < p.N) dst[j] = p.alpha * __uint_as_float(v[j]);
             }
           }
         }

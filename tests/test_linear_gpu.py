@@ -190,3 +190,48 @@ def test_empty_batch_returns_empty_output_and_zero_grads():
     y.sum().backward()
     assert x.grad.shape == x.shape
     assert float(layer.downscale_weights[0].grad.abs().max()) == 0.0 and float(layer.bias.grad.abs().max()) == 0.0
+
+
+def test_backward_is_bit_reproducible():
+    """dA / dB contract over T with split-K; the partial sums are reduced in a fixed order (no fp32 atomics), so two
+    backward passes over the same inputs give identical bits -- as the reference's cuBLAS path does."""
+    from tn_gradient.layer.sow import SoWLinear
+    torch.manual_seed(0)
+    layer = SoWLinear(1024, 2736, bias=True, rank=50, init_method="normal", dtype=torch.bfloat16, device="cuda")
+    layer.acc_downweight = torch.nn.Parameter((torch.randn(1024, 2736, device="cuda") * 0.02).bfloat16(), requires_grad=False)
+    with torch.no_grad():
+        layer.upscale_weights[0].normal_(0, 0.05)
+    x = torch.randn(8192, 1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    dy = torch.randn(8192, 2736, device="cuda", dtype=torch.bfloat16)
+    runs = []
+    for _ in range(3):
+        x.grad = None
+        layer.zero_grad()
+        layer(x).backward(dy)
+        runs.append([x.grad.clone(), layer.downscale_weights[0].grad.clone(), layer.upscale_weights[0].grad.clone(),
+                     layer.bias.grad.clone()])
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert torch.equal(a, b)
+
+
+def test_backward_as_first_cuda_work_of_the_autograd_thread():
+    """The first node autograd's worker thread runs may be ours: no CUDA call has bound a context to that thread yet, and the
+    TMA descriptor encode (a driver call) needs one.  Fresh shapes defeat the descriptor cache."""
+    import threading
+    from tn_gradient.layer.sow import SoWLinear
+    out = {}
+
+    def body():
+        layer = SoWLinear(328, 456, bias=False, rank=8, init_method="normal", dtype=torch.bfloat16, device="cuda")
+        x = torch.randn(77, 328, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        dy = torch.randn(77, 456, device="cuda", dtype=torch.bfloat16)
+        y = layer(x)
+        y.backward(dy)                     # backward thread: first work is sow_linear_bwd_factors on new pointers
+        torch.cuda.synchronize()
+        out["ok"] = bool(torch.isfinite(x.grad.float()).all())
+
+    th = threading.Thread(target=body)
+    th.start()
+    th.join()
+    assert out.get("ok") is True
