@@ -133,6 +133,7 @@ int sow_adam_multi_ex(const void* chunks_dev, int n_chunks, int64_t total_elems,
                       int dtype, void* stream_) {
   if (n_chunks <= 0) return SOWB_OK;
   SOWB_REQUIRE(chunks_dev != nullptr, "sow_adam_multi: null chunk table");
+  if (int rc0 = ensure_context_for(chunks_dev)) return rc0;
   SOWB_REQUIRE(bias_correction1 > 0.0 && bias_correction2 > 0.0, "sow_adam_multi: bias corrections must be positive");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   AdamHyper h;

@@ -540,6 +540,7 @@ int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* t
   if (n <= 0) return SOWB_OK;
   if (dtype != SOWB_BF16) return set_error(SOWB_EINVAL, "sow_merge_grouped: only SOWB_BF16 is implemented");
   SOWB_REQUIRE(entries != nullptr && table_dev != nullptr, "sow_merge_grouped: null pointer argument");
+  if (int rc0 = ensure_context_for(table_dev)) return rc0;
   SOWB_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 127) == 0, "sow_merge_grouped: table_dev must be 128-byte aligned");
   int rc = require_sm100();
   if (rc) return rc;

@@ -991,6 +991,7 @@ static int adam2_common(bool head, void* p, const void* g, const float* G1m, con
                         double step_size_d, double lr_wd_d, int first_step, int dtype, void* stream_) {
   const float beta1 = float(beta1_d), beta2 = float(beta2_d), omb1 = float(1.0 - beta1_d), omb2 = float(1.0 - beta2_d);
   SOWB_REQUIRE(g != nullptr, "tt_adam2: null gradient pointer");
+  if (int rc0 = ensure_context_for(g)) return rc0;
   SOWB_REQUIRE(first_step || (G1m && G2m && G1v && G2v), "tt_adam2: null core pointer");
   SOWB_REQUIRE(r > 0 && r <= 64, "tt_adam2: rank %d unsupported (1..64)", r);
   SOWB_REQUIRE(int64_t(mm) * mm >= M && int64_t(nn) * nn >= N, "tt_adam2: mm/nn too small for (M,N)");
@@ -1023,6 +1024,7 @@ int tt_adam2_fused(void* p, const void* g, const float* G1m, const float* G2m, c
 int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64_t q_batch_stride, int m, int r,
                 int batch, void* ws, size_t ws_bytes, void* stream_) {
   SOWB_REQUIRE(X && Q && ws, "sow_thin_qr: null pointer argument");
+  if (int rc0 = ensure_context_for(X)) return rc0;
   SOWB_REQUIRE(m > 0 && r > 0 && batch > 0 && ldx >= r, "sow_thin_qr: bad dimensions (m=%d r=%d ldx=%d batch=%d)", m, r, ldx, batch);
   SOWB_REQUIRE(r <= m, "sow_thin_qr: rank %d exceeds the row count %d (the reference fails here too: tt.py:135)", r, m);
   SOWB_REQUIRE(r <= 4096, "sow_thin_qr: rank %d too large", r);
@@ -1055,6 +1057,7 @@ int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64
 int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q_batch_stride, float* R,
                int64_t r_batch_stride, int m, int n, int r, int batch, void* stream_) {
   SOWB_REQUIRE(L && Q && R, "tt_project: null pointer argument");
+  if (int rc0 = ensure_context_for(L)) return rc0;
   SOWB_REQUIRE(m > 0 && n > 0 && r > 0 && batch > 0, "tt_project: bad dimensions");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int n_tiles = ceil_div(n, kPjTN);
@@ -1079,6 +1082,7 @@ int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q
 
 int tt_interleave(const void* src, int M, int N, int mm, int nn, int order, float* out, int dtype, void* stream_) {
   SOWB_REQUIRE(src && out, "tt_interleave: null pointer argument");
+  if (int rc0 = ensure_context_for(src)) return rc0;
   SOWB_REQUIRE(order >= 1 && order <= 8 && mm > 0 && nn > 0, "tt_interleave: bad order/shape");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int64_t total = 1;
@@ -1095,6 +1099,7 @@ int tt_interleave(const void* src, int M, int N, int mm, int nn, int order, floa
 
 int tt_deinterleave(const float* src, int M, int N, int mm, int nn, int order, void* out, int dtype, void* stream_) {
   SOWB_REQUIRE(src && out, "tt_deinterleave: null pointer argument");
+  if (int rc0 = ensure_context_for(src)) return rc0;
   SOWB_REQUIRE(order >= 1 && order <= 8 && mm > 0 && nn > 0, "tt_deinterleave: bad order/shape");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int64_t total = 1;
@@ -1111,6 +1116,7 @@ int tt_deinterleave(const float* src, int M, int N, int mm, int nn, int order, v
 
 int tt_matmul_rk(const float* A, const float* B, float* C, int m, int n, int r, void* stream_) {
   SOWB_REQUIRE(A && B && C, "tt_matmul_rk: null pointer argument");
+  if (int rc0 = ensure_context_for(A)) return rc0;
   SOWB_REQUIRE(m > 0 && n > 0 && r > 0, "tt_matmul_rk: bad dimensions");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   dim3 grid(ceil_div(n, kRkTile), ceil_div(m, kRkTile));
@@ -1127,6 +1133,7 @@ int tt_adam_fused2(void* p, const void* g, const float* G1m, const float* G2m, c
   const float beta1 = float(beta1_d), beta2 = float(beta2_d), omb1 = float(1.0 - beta1_d), omb2 = float(1.0 - beta2_d);
   const float eps = float(eps_d), step_size = float(step_size_d), lr_wd = float(lr_wd_d);
   SOWB_REQUIRE(p && g && m_out && v_out, "tt_adam_fused2: null pointer argument");
+  if (int rc0 = ensure_context_for(g)) return rc0;
   SOWB_REQUIRE(first_step || (G1m && G2m && G1v && G2v), "tt_adam_fused2: null core pointer");
   SOWB_REQUIRE(r > 0 && r <= 128, "tt_adam_fused2: rank %d unsupported (1..128)", r);
   SOWB_REQUIRE(int64_t(mm) * mm >= M && int64_t(nn) * nn >= N, "tt_adam_fused2: mm/nn too small for (M,N)");
@@ -1156,6 +1163,7 @@ int tt_adam_dense(void* p, const void* g, float* m, float* v, int64_t numel, dou
   const float beta1 = float(beta1_d), beta2 = float(beta2_d), omb1 = float(1.0 - beta1_d), omb2 = float(1.0 - beta2_d);
   const float eps = float(eps_d), step_size = float(step_size_d), lr_wd = float(lr_wd_d);
   SOWB_REQUIRE(p && g && m && v && numel > 0, "tt_adam_dense: bad argument");
+  if (int rc0 = ensure_context_for(g)) return rc0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (dtype == SOWB_BF16)
     tt_adam_dense_kernel<__nv_bfloat16><<<grid_for(numel, 256), 256, 0, stream>>>(

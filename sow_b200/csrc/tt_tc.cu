@@ -525,6 +525,7 @@ int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, co
                   double eps, double step_size, double lr_wd, int first_step, int dtype, void* ws, size_t ws_bytes,
                   void* stream_) {
   SOWB_REQUIRE(p && g && Qm && Qv && Rm && Rv && ws, "tt_adam2_step: null pointer argument");
+  if (int rc0 = ensure_context_for(g)) return rc0;
   SOWB_REQUIRE(first_step || (G1m && G2m && G1v && G2v), "tt_adam2_step: null core pointer");
   SOWB_REQUIRE(r > 0 && r <= 64, "tt_adam2_step: rank %d unsupported (1..64)", r);
   SOWB_REQUIRE(int64_t(mm) * mm >= M && int64_t(nn) * nn >= N, "tt_adam2_step: mm/nn too small for (M,N)");
