@@ -300,7 +300,10 @@ def main():
     extra_kernels = {
         "merge": {"bound": "hbm", "achieved": merge_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                   "frac": merge_gbs / peaks["hbm_gbs"], "ms": mg_ms, "algorithmic_bytes": mg_bytes, "launches": mg_n,
-                  "events": len(merge_ms), "ms_all": merge_ms},
+                  "events": len(merge_ms), "ms_all": merge_ms,
+                  # dram__bytes_read + dram__bytes_write of one launch, ncu --set full (profiles/r01_merge_v3_ncu_full_summary.csv:
+                  # 729 MB + 553 MB; the rest of the written data is still dirty in L2 when the kernel ends)
+                  "traffic": 1.282e9 if abs(mg_bytes - 1256265216.0) < 1 else None},
     }
     extra_kernels.update(tt_rows)
     for k in ("gemm_skinny", "gemm_splitk", "adam"):
