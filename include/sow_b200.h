@@ -133,6 +133,18 @@ int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q
 int tt_interleave(const void* src, int M, int N, int mm, int nn, int order, float* out, int dtype, void* stream);
 int tt_deinterleave(const float* src, int M, int N, int mm, int nn, int order, void* out, int dtype, void* stream);
 
+/*
+ * Order-2 TT of a matrix without materialising the padded + interleaved unfolding (tt.py:48-67 pads, reshapes and permutes:
+ * three passes over M.N).  Element (ga, gb) of the P x P unfolding (P = mm*nn, ga = i1*nn + o1, gb = i2*nn + o2) is source
+ * element (i1*mm + i2, o1*nn + o2), zero outside (M, N); the kernels address the source directly.
+ *   tt_gather2      : X[P, ncols] = first ncols columns of the unfolding (input of sow_thin_qr)
+ *   tt_project2     : R[r, P] = Q[P, r]^T . unfolding                     (TensorTrain.decompose, tt.py:129-133)
+ *   tt_reconstruct2 : dst[M, N] = (G1[P, r] . G2[r, P]) de-interleaved and un-padded   (TensorTrain.to_matrix, tt.py:242-247)
+ */
+int tt_gather2(const void* src, int M, int N, int mm, int nn, float* X, int ncols, int dtype, void* stream);
+int tt_project2(const void* src, int M, int N, int mm, int nn, const float* Q, float* R, int r, int dtype, void* stream);
+int tt_reconstruct2(const float* G1, const float* G2, int r, void* dst, int M, int N, int mm, int nn, int dtype, void* stream);
+
 /* fp32 C[m,n] = A[m,r] . B[r,n] with small r: one link of the reconstruction chain (tt.py:213-237). */
 int tt_matmul_rk(const float* A, const float* B, float* C, int m, int n, int r, void* stream);
 

@@ -59,6 +59,9 @@ SIGNATURES = {
     "tt_project": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
     "tt_interleave": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "tt_deinterleave": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "tt_gather2": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "tt_project2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "tt_reconstruct2": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "tt_matmul_rk": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "tt_adam_fused2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i, _vp]),
     "tt_adam2_head": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _vp]),

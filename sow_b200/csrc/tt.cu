@@ -538,10 +538,194 @@ __global__ void tt_deinterleave_kernel(const float* __restrict__ src, int M, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Order-2 TT of a matrix WITHOUT materialising the padded + interleaved unfolding (tt.py:48-67 builds it with pad,
+// reshape and permute = three passes over M.N): element (ga, gb) of the P x P unfolding, ga = i1*nn + o1, gb = i2*nn + o2,
+// is source element (i1*mm + i2, o1*nn + o2) (zero outside (M, N)), so the kernels below address the source directly.
+//   tt_gather2   : X[P, ncols]  = first ncols columns of the unfolding     (input of the thin QR)
+//   tt_project2  : R[r, P]      = Q[P, r]^T . unfolding                    (one pass over the source)
+//   tt_reconstruct2 : dst[M, N] = (G1 . G2) de-interleaved and un-padded   (TensorTrain.to_matrix, tt.py:242-247)
+// ------------------------------------------------------------------------------------------------
+constexpr int kRkTile = 64;
+
+template <typename T>
+__global__ void tt_gather2_kernel(const T* __restrict__ src, int M, int N, int mm, int nn, float* __restrict__ X, int ncols) {
+  const int P = mm * nn;
+  const int64_t total = static_cast<int64_t>(P) * ncols;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ga = static_cast<int>(idx / ncols), gb = static_cast<int>(idx - static_cast<int64_t>(ga) * ncols);
+    const int i1 = ga / nn, o1 = ga - i1 * nn, i2 = gb / nn, o2 = gb - i2 * nn;
+    const int64_t row = static_cast<int64_t>(i1) * mm + i2, col = static_cast<int64_t>(o1) * nn + o2;
+    X[idx] = (gb < P && row < M && col < N) ? load_as_f32<T>(src, row * N + col) : 0.f;
+  }
+}
+
+// Same tiling as tt_project_kernel (64 x 128 tile, 4 x (4 + 4) outputs per thread, 16-byte shared-memory operands,
+// register prefetch of the next K stage); only the fetch differs: the unfolding is read through the index map.
+template <typename T>
+__global__ void __launch_bounds__(kPjThreads)
+tt_project2_kernel(const T* __restrict__ src, int M, int N, int mm, int nn, const float* __restrict__ Q,
+                   float* __restrict__ R, int r, int m_per_split) {
+  __shared__ __align__(16) float sL[kPjTM][kPjTN];
+  __shared__ __align__(16) float sQ[kPjTM][kPjRT];
+  __shared__ int64_t s_colpart[kPjTN];
+  __shared__ int s_coli2[kPjTN], s_colo2[kPjTN];
+  const int P = mm * nn;
+  const int n0 = blockIdx.x * kPjTN;
+  const int m_begin = blockIdx.y * m_per_split;
+  const int m_end = min(P, m_begin + m_per_split);
+  const int tid = threadIdx.x;
+  const int tr = tid / 16, tn = tid % 16;
+  if (tid < kPjTN) {
+    const int gb = n0 + tid;
+    const int i2 = gb / nn, o2 = gb - i2 * nn;
+    s_coli2[tid] = (gb < P) ? i2 : (1 << 28);
+    s_colo2[tid] = o2;
+    s_colpart[tid] = static_cast<int64_t>(i2) * N + o2;
+  }
+  __syncthreads();
+  float pl[16];
+  float pq[8];
+  for (int r0 = 0; r0 < r; r0 += kPjRT) {
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+    auto fetch = [&](int mm0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = tid + u * kPjThreads;          // 0..1023: row i, column group c4
+        const int i = idx >> 5, c4 = (idx & 31) * 4;
+        const int ga = mm0 + i;
+        const int i1 = ga / nn, o1 = ga - i1 * nn;
+        const int64_t rowbase = static_cast<int64_t>(i1) * mm * N + static_cast<int64_t>(o1) * nn;
+        const int rlim = (ga < m_end) ? M - i1 * mm : 0;
+        const int clim = N - o1 * nn;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c4 + e;
+          const bool ok = s_coli2[c] < rlim && s_colo2[c] < clim;
+          pl[u * 4 + e] = ok ? load_as_f32<T>(src, rowbase + s_colpart[c]) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = tid + u * kPjThreads;          // 0..2047
+        const int i = idx >> 6, k = idx & 63;
+        const int gi = mm0 + i, gk = r0 + k;
+        pq[u] = (gi < m_end && gk < r) ? Q[static_cast<int64_t>(gi) * r + gk] : 0.f;
+      }
+    };
+    auto stash = [&]() {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = tid + u * kPjThreads;
+        *reinterpret_cast<float4*>(&sL[idx >> 5][(idx & 31) * 4]) = make_float4(pl[u * 4], pl[u * 4 + 1], pl[u * 4 + 2], pl[u * 4 + 3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = tid + u * kPjThreads;
+        sQ[idx >> 6][idx & 63] = pq[u];
+      }
+    };
+    if (m_begin < m_end) fetch(m_begin);
+    for (int mm0 = m_begin; mm0 < m_end; mm0 += kPjTM) {
+      stash();
+      __syncthreads();
+      if (mm0 + kPjTM < m_end) fetch(mm0 + kPjTM);
+#pragma unroll 8
+      for (int i = 0; i < kPjTM; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(&sQ[i][tr * 4]);
+        const float4 l0 = *reinterpret_cast<const float4*>(&sL[i][tn * 4]);
+        const float4 l1 = *reinterpret_cast<const float4*>(&sL[i][64 + tn * 4]);
+        const float qv[4] = {q.x, q.y, q.z, q.w};
+        const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(qv[a], lv[c], acc[a][c]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int gr = r0 + tr * 4 + a;
+      if (gr >= r) continue;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int gc = n0 + (c < 4 ? tn * 4 + c : 64 + tn * 4 + (c - 4));
+        if (gc < P) {
+          if (gridDim.y == 1) R[static_cast<int64_t>(gr) * P + gc] = acc[a][c];
+          else atomicAdd(&R[static_cast<int64_t>(gr) * P + gc], acc[a][c]);
+        }
+      }
+    }
+  }
+}
+
+// C = G1 [P, r] . G2 [r, P], written straight to dst[M, N] through the index map (only the (M, N) window is stored).
+template <typename T>
+__global__ void __launch_bounds__(256)
+tt_reconstruct2_kernel(const float* __restrict__ G1, const float* __restrict__ G2, int r, T* __restrict__ dst, int M, int N,
+                       int mm, int nn) {
+  __shared__ float sA[kRkTile][kRkTile + 1];  // [row][k]
+  __shared__ float sB[kRkTile][kRkTile];      // [k][col]
+  const int P = mm * nn;
+  const int m0 = blockIdx.y * kRkTile, n0 = blockIdx.x * kRkTile;
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+  for (int k0 = 0; k0 < r; k0 += kRkTile) {
+    for (int idx = tid; idx < kRkTile * kRkTile; idx += 256) {
+      const int i = idx / kRkTile, k = idx % kRkTile;
+      sA[i][k] = (m0 + i < P && k0 + k < r) ? G1[static_cast<int64_t>(m0 + i) * r + k0 + k] : 0.f;
+      const int kk = idx / kRkTile, c = idx % kRkTile;
+      sB[kk][c] = (k0 + kk < r && n0 + c < P) ? G2[static_cast<int64_t>(k0 + kk) * P + n0 + c] : 0.f;
+    }
+    __syncthreads();
+    const int kn = min(kRkTile, r - k0);
+    for (int k = 0; k < kn; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = sA[ty * 4 + a][k];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = sB[k][tx + 16 * c];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+    }
+    __syncthreads();
+  }
+  int ci2[4], co2[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int gb = n0 + tx + 16 * c;
+    ci2[c] = gb / nn;
+    co2[c] = gb - ci2[c] * nn;
+    if (gb >= P) ci2[c] = 1 << 28;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int ga = m0 + ty * 4 + a;
+    if (ga >= P) continue;
+    const int i1 = ga / nn, o1 = ga - i1 * nn;
+    const int rlim = M - i1 * mm, clim = N - o1 * nn;
+    const int64_t rowbase = static_cast<int64_t>(i1) * mm * N + static_cast<int64_t>(o1) * nn;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (ci2[c] < rlim && co2[c] < clim) store_from_f32<T>(dst, rowbase + static_cast<int64_t>(ci2[c]) * N + co2[c], acc[a][c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // small-K fp32 matmul  C[m, n] = A[m, r] . B[r, n]   (TT reconstruction chain, tt.py:213-237)
 // 64 x 64 output tile per CTA, 4 x 4 per thread, whole K (= r <= 64 per pass) in smem.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRkTile = 64;
 __global__ void __launch_bounds__(256)
 tt_matmul_rk_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int m, int n, int r) {
   __shared__ float sA[kRkTile][kRkTile + 1];  // [row][k]
@@ -1076,6 +1260,64 @@ int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q
   }
   dim3 grid(n_tiles, splits, batch);
   tt_project_kernel<<<grid, kPjThreads, 0, stream>>>(L, l_batch_stride, Q, q_batch_stride, R, r_batch_stride, m, n, r, m_per);
+  SOWB_CHECK_CUDA(cudaGetLastError());
+  return SOWB_OK;
+}
+
+int tt_gather2(const void* src, int M, int N, int mm, int nn, float* X, int ncols, int dtype, void* stream_) {
+  SOWB_REQUIRE(src && X, "tt_gather2: null pointer argument");
+  SOWB_REQUIRE(mm > 0 && nn > 0 && ncols > 0 && int64_t(mm) * mm >= M && int64_t(nn) * nn >= N, "tt_gather2: bad shape");
+  if (int rc0 = ensure_context_for(src)) return rc0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t total = int64_t(mm) * nn * ncols;
+  if (dtype == SOWB_BF16)
+    tt_gather2_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), M, N, mm, nn, X, ncols);
+  else if (dtype == SOWB_F32)
+    tt_gather2_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), M, N, mm, nn, X, ncols);
+  else
+    return set_error(SOWB_EINVAL, "tt_gather2: unknown dtype %d", dtype);
+  SOWB_CHECK_CUDA(cudaGetLastError());
+  return SOWB_OK;
+}
+
+int tt_project2(const void* src, int M, int N, int mm, int nn, const float* Q, float* R, int r, int dtype, void* stream_) {
+  SOWB_REQUIRE(src && Q && R, "tt_project2: null pointer argument");
+  SOWB_REQUIRE(mm > 0 && nn > 0 && r > 0 && int64_t(mm) * mm >= M && int64_t(nn) * nn >= N, "tt_project2: bad shape");
+  if (int rc0 = ensure_context_for(src)) return rc0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int P = mm * nn;
+  const int n_tiles = ceil_div(P, kPjTN);
+  int splits = std::max(1, (2 * num_sms()) / std::max(1, n_tiles));
+  splits = std::min(splits, ceil_div(P, 4 * kPjTM));
+  splits = std::max(1, std::min(splits, 65535));
+  const int m_per = round_up(ceil_div(P, splits), kPjTM);
+  splits = ceil_div(P, m_per);
+  if (splits > 1) SOWB_CHECK_CUDA(cudaMemsetAsync(R, 0, size_t(r) * P * 4, stream));
+  dim3 grid(n_tiles, splits);
+  if (dtype == SOWB_BF16)
+    tt_project2_kernel<__nv_bfloat16><<<grid, kPjThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), M, N, mm, nn, Q, R, r, m_per);
+  else if (dtype == SOWB_F32)
+    tt_project2_kernel<float><<<grid, kPjThreads, 0, stream>>>(static_cast<const float*>(src), M, N, mm, nn, Q, R, r, m_per);
+  else
+    return set_error(SOWB_EINVAL, "tt_project2: unknown dtype %d", dtype);
+  SOWB_CHECK_CUDA(cudaGetLastError());
+  return SOWB_OK;
+}
+
+int tt_reconstruct2(const float* G1, const float* G2, int r, void* dst, int M, int N, int mm, int nn, int dtype, void* stream_) {
+  SOWB_REQUIRE(G1 && G2 && dst, "tt_reconstruct2: null pointer argument");
+  SOWB_REQUIRE(mm > 0 && nn > 0 && r > 0 && int64_t(mm) * mm >= M && int64_t(nn) * nn >= N, "tt_reconstruct2: bad shape");
+  if (int rc0 = ensure_context_for(G1)) return rc0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int P = mm * nn;
+  dim3 grid(ceil_div(P, kRkTile), ceil_div(P, kRkTile));
+  SOWB_REQUIRE(grid.y <= 65535, "tt_reconstruct2: unfolding too large");
+  if (dtype == SOWB_BF16)
+    tt_reconstruct2_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(G1, G2, r, static_cast<__nv_bfloat16*>(dst), M, N, mm, nn);
+  else if (dtype == SOWB_F32)
+    tt_reconstruct2_kernel<float><<<grid, 256, 0, stream>>>(G1, G2, r, static_cast<float*>(dst), M, N, mm, nn);
+  else
+    return set_error(SOWB_EINVAL, "tt_reconstruct2: unknown dtype %d", dtype);
   SOWB_CHECK_CUDA(cudaGetLastError());
   return SOWB_OK;
 }

@@ -229,6 +229,40 @@ def deinterleave(src: torch.Tensor, M: int, N: int, mm: int, nn: int, order: int
     return out
 
 
+def decompose2(src: torch.Tensor, mm: int, nn: int, r: int):
+    """Order-2 TT of a (M,N) bf16/fp32 matrix without materialising the interleaved unfolding: returns
+    (Q (P,r), R (r,P)) fp32 with P = mm*nn (include/sow_b200.h: tt_gather2 / sow_thin_qr / tt_project2)."""
+    _require_cuda(src)
+    lib = _lib.load()
+    src = src.contiguous()
+    M, N = src.shape
+    P = mm * nn
+    dt = _dtype_code(src.dtype)
+    st = _stream_ptr(src.device)
+    ncols = min(P, (r + 7) // 8 * 8)
+    X = torch.empty((P, ncols), dtype=torch.float32, device=src.device)
+    check(lib.tt_gather2(_p(src), M, N, mm, nn, _p(X), ncols, dt, st), "tt_gather2")
+    Q = thin_qr(X, r)
+    R = torch.empty((r, P), dtype=torch.float32, device=src.device)
+    check(lib.tt_project2(_p(src), M, N, mm, nn, _p(Q), _p(R), r, dt, st), "tt_project2")
+    launch_counter["kernels"] += 3
+    return Q, R
+
+
+def reconstruct2(G1: torch.Tensor, G2: torch.Tensor, M: int, N: int, mm: int, nn: int, dtype=torch.float32) -> torch.Tensor:
+    """(M,N) window of the order-2 TT (G1 (P,r), G2 (r,P)), written de-interleaved in one pass."""
+    _require_cuda(G1, G2)
+    lib = _lib.load()
+    G1 = G1.contiguous()
+    G2 = G2.contiguous()
+    r = G1.shape[1]
+    out = torch.empty((M, N), dtype=dtype, device=G1.device)
+    check(lib.tt_reconstruct2(_p(G1), _p(G2), r, _p(out), M, N, mm, nn, _dtype_code(dtype), _stream_ptr(G1.device)),
+          "tt_reconstruct2")
+    launch_counter["kernels"] += 1
+    return out
+
+
 def matmul_rk(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     """fp32 C = A (m,r) . B (r,n) for small r."""
     _require_cuda(A, B)

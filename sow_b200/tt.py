@@ -106,8 +106,18 @@ class TensorTrain:
         src = matrix.detach()
         if src.dtype not in (torch.float32, torch.bfloat16):
             src = src.to(torch.float32)
-        flat = ops.interleave(src, mm, nn_, order)
         tt = TensorTrain(ranks, (mm,) * order, (nn_,) * order)
+        if order == 2:
+            # the unfolding is addressed through the index map: no padded / interleaved copy of the matrix at all
+            r = ranks[1]
+            if r > mm * nn_:
+                raise RuntimeError(f"TT rank {r} exceeds the unfolding row count {mm * nn_} at core 0 "
+                                   "(the reference raises a reshape error here, tt.py:135)")
+            Q, R = ops.decompose2(src, mm, nn_, r)
+            tt.cores = [Q.reshape(1, mm, nn_, r), R.reshape(r, mm, nn_, 1)]
+            tt.device = matrix.device
+            return tt
+        flat = ops.interleave(src, mm, nn_, order)
         tt._decompose_interleaved(flat)
         return tt.to(matrix.device)
 
@@ -204,6 +214,12 @@ class TensorTrain:
 
     def to_matrix(self, shape) -> torch.Tensor:
         d = self.order
+        if d == 2 and _uniform(self.input_shape) and _uniform(self.output_shape) and self.cores[0].is_cuda:
+            mm, nn_ = int(self.input_shape[0]), int(self.output_shape[0])
+            c0, c1 = self.cores
+            G1 = c0.detach().to(torch.float32).reshape(mm * nn_, -1)
+            G2 = c1.detach().to(torch.float32).reshape(-1, mm * nn_)
+            return ops.reconstruct2(G1, G2, min(int(shape[0]), mm * mm), min(int(shape[1]), nn_ * nn_), mm, nn_)
         if _uniform(self.input_shape) and _uniform(self.output_shape) and self.cores[0].is_cuda:
             # fused de-interleave + unpad: only the (M, N) window is written
             c0 = self.cores[0]
