@@ -193,6 +193,14 @@ int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, co
                   double eps, double step_size, double lr_wd, int first_step, int dtype, void* ws, size_t ws_bytes,
                   void* stream);
 
+/*
+ * TT-Adam update for order > 2 on moments kept in the interleaved layout of tt_interleave ((mm*nn)^order fp32 elements each,
+ * updated in place): the reconstruction chain already produces that layout and the decomposition sweep consumes it, so the
+ * dense (M,N) moments of ttadam.py:71-84,113-115 never exist.  Padded positions are set to 0; v is clamped at 0 first.
+ */
+int tt_adam_interleaved(void* p, const void* g, float* m, float* v, int M, int N, int mm, int nn, int order, double beta1,
+                        double beta2, double eps, double step_size, double lr_wd, int dtype, void* stream);
+
 /* Same update on dense fp32 moments m, v of shape (M,N) (order > 2 path); v is clamped at 0 first (ttadam.py:84). */
 int tt_adam_dense(void* p, const void* g, float* m, float* v, int64_t numel, double beta1, double beta2, double eps,
                   double step_size, double lr_wd, int dtype, void* stream);

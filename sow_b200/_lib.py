@@ -69,6 +69,7 @@ SIGNATURES = {
     "tt_adam2_workspace_bytes": (_sz, [_i, _i]),
     "tt_adam2_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i,
                            _vp, _sz, _vp]),
+    "tt_adam_interleaved": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _vp]),
     "tt_adam_dense": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _vp]),
     "sow_adam_chunk_elems": (_i, []),
     "sow_adam_multi_ex": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _d, _d, _i, _i, _vp]),

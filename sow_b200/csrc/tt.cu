@@ -1110,6 +1110,38 @@ __global__ void tt_adam_dense_kernel(T* __restrict__ p, const T* __restrict__ g,
   }
 }
 
+// Dense TT-Adam for order > 2 on moments kept in the INTERLEAVED layout (the layout the reconstruction chain produces and
+// the decomposition sweep consumes): m, v are fp32 tensors of (mm*nn)^order elements in (i1,o1,...,id,od) order, updated
+// in place; p and g are addressed through the index map; padded positions get m = v = 0 (the reference crops the
+// reconstruction to (M, N) and zero-pads again, ttadam.py:71-84 + tt.py:48-58).  Saves the de-interleave of both
+// reconstructed moments and the interleave of both updated moments: four passes over the padded matrix per step.
+template <typename T>
+__global__ void tt_adam_interleaved_kernel(T* __restrict__ p, const T* __restrict__ g, float* __restrict__ m,
+                                           float* __restrict__ v, int M, int N, FastDiv fm, FastDiv fn, int order,
+                                           int64_t total, float beta1, float omb1, float beta2, float omb2, float eps,
+                                           float step_size, float lr_wd) {
+  const bool small = total < (int64_t(1) << 32);
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t row, col;
+    if (small) decode_interleaved(static_cast<uint32_t>(idx), fm, fn, order, row, col);
+    else decode_interleaved64(idx, fm.d, fn.d, order, row, col);
+    float mo = 0.f, vo = 0.f;
+    if (row < M && col < N) {
+      const int64_t e = row * N + col;
+      const float gv = load_as_f32<T>(g, e);
+      float pv = load_as_f32<T>(p, e);
+      mo = beta1 * m[idx] + omb1 * gv;                                   // ttadam.py:92
+      vo = beta2 * fmaxf(v[idx], 0.f) + omb2 * gv * gv;                  // ttadam.py:84,93
+      pv -= step_size * (mo / (sqrtf(vo) + eps));                        // ttadam.py:94,103,108
+      if (lr_wd > 0.f) pv -= lr_wd * pv;                                 // ttadam.py:110-111
+      store_from_f32<T>(p, e, pv);
+    }
+    m[idx] = mo;
+    v[idx] = vo;
+  }
+}
+
 static inline int grid_for(int64_t n, int threads) {
   const int64_t b = (n + threads - 1) / threads;
   return static_cast<int>(std::min<int64_t>(b, int64_t(num_sms()) * 16));
@@ -1396,6 +1428,30 @@ int tt_adam_fused2(void* p, const void* g, const float* G1m, const float* G2m, c
   } else {
     return set_error(SOWB_EINVAL, "tt_adam_fused2: unknown dtype %d", dtype);
   }
+  SOWB_CHECK_CUDA(cudaGetLastError());
+  return SOWB_OK;
+}
+
+int tt_adam_interleaved(void* p, const void* g, float* m, float* v, int M, int N, int mm, int nn, int order, double beta1_d,
+                        double beta2_d, double eps_d, double step_size_d, double lr_wd_d, int dtype, void* stream_) {
+  const float beta1 = float(beta1_d), beta2 = float(beta2_d), omb1 = float(1.0 - beta1_d), omb2 = float(1.0 - beta2_d);
+  const float eps = float(eps_d), step_size = float(step_size_d), lr_wd = float(lr_wd_d);
+  SOWB_REQUIRE(p && g && m && v, "tt_adam_interleaved: null pointer argument");
+  SOWB_REQUIRE(order >= 1 && order <= 8 && mm > 0 && nn > 0, "tt_adam_interleaved: bad order/shape");
+  if (int rc0 = ensure_context_for(g)) return rc0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int64_t total = 1;
+  for (int k = 0; k < order; ++k) total *= int64_t(mm) * nn;
+  if (dtype == SOWB_BF16)
+    tt_adam_interleaved_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
+        static_cast<__nv_bfloat16*>(p), static_cast<const __nv_bfloat16*>(g), m, v, M, N, make_fastdiv(mm), make_fastdiv(nn),
+        order, total, beta1, omb1, beta2, omb2, eps, step_size, lr_wd);
+  else if (dtype == SOWB_F32)
+    tt_adam_interleaved_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(
+        static_cast<float*>(p), static_cast<const float*>(g), m, v, M, N, make_fastdiv(mm), make_fastdiv(nn), order, total,
+        beta1, omb1, beta2, omb2, eps, step_size, lr_wd);
+  else
+    return set_error(SOWB_EINVAL, "tt_adam_interleaved: unknown dtype %d", dtype);
   SOWB_CHECK_CUDA(cudaGetLastError());
   return SOWB_OK;
 }

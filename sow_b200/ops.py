@@ -328,6 +328,18 @@ def tt_adam2_step(p, g, cores_m, cores_v, mm, nn, r, beta1, beta2, eps, step_siz
     return (Q[0], R[0]), (Q[1], R[1])
 
 
+def tt_adam_interleaved(p, g, m, v, mm, nn, order, beta1, beta2, eps, step_size, lr_wd):
+    """In-place TT-Adam on interleaved fp32 moments m, v ((mm*nn)^order elements each); p, g are (M,N)."""
+    _require_cuda(p, g, m, v)
+    lib = _lib.load()
+    g = g.contiguous()
+    M, N = p.shape
+    rc = lib.tt_adam_interleaved(_p(p), _p(g), _p(m), _p(v), M, N, mm, nn, order, float(beta1), float(beta2), float(eps),
+                                 float(step_size), float(lr_wd), _dtype_code(p.dtype), _stream_ptr(p.device))
+    check(rc, "tt_adam_interleaved")
+    launch_counter["kernels"] += 1
+
+
 def tt_adam_dense(p, g, m, v, beta1, beta2, eps, step_size, lr_wd):
     _require_cuda(p, g, m, v)
     lib = _lib.load()

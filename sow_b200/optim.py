@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import SowB200Error
-from .tt import TensorTrain
+from .tt import TensorTrain, reconstruct_interleaved
 
 
 class TTAdam(torch.optim.Optimizer):
@@ -116,15 +116,20 @@ class TTAdam(torch.optim.Optimizer):
                 tt.cores = [Q[b].reshape(1, mm, nn_, r), R[b].reshape(r, mm, nn_, 1)]
                 state[key] = tt
             return
+        # order > 2: the moments stay in the interleaved layout between the reconstruction chain, the Adam kernel and the
+        # decomposition sweep (no de-interleave / interleave passes; ttadam.py:71-84,113-115)
+        total = (mm * nn_) ** order
         if first:
-            m = torch.zeros((M, N), dtype=torch.float32, device=pd.device)
-            v = torch.zeros((M, N), dtype=torch.float32, device=pd.device)
+            m = torch.zeros((total,), dtype=torch.float32, device=pd.device)
+            v = torch.zeros((total,), dtype=torch.float32, device=pd.device)
         else:
-            m = state["exp_avg"].to_matrix((M, N))                           # ttadam.py:71-74
-            v = state["exp_avg_sq"].to_matrix((M, N))                        # ttadam.py:79-84 (clamp in kernel)
-        ops.tt_adam_dense(pd, g, m, v, beta1, beta2, eps, step_size, lr_wd)
-        state["exp_avg"] = TensorTrain.from_matrix(m, ranks=ranks, padding=True)      # ttadam.py:113-115
-        state["exp_avg_sq"] = TensorTrain.from_matrix(v, ranks=ranks, padding=True)
+            m = reconstruct_interleaved(state["exp_avg"].cores)
+            v = reconstruct_interleaved(state["exp_avg_sq"].cores)
+        ops.tt_adam_interleaved(pd, g, m, v, mm, nn_, order, beta1, beta2, eps, step_size, lr_wd)
+        for key, flat in (("exp_avg", m), ("exp_avg_sq", v)):
+            tt = TensorTrain(list(ranks), (mm,) * order, (nn_,) * order, device=pd.device)
+            tt._decompose_interleaved(flat)
+            state[key] = tt
 
 
 class TTRAdam(torch.optim.Optimizer):

@@ -39,6 +39,19 @@ class _Contraction:
         return _reconstruct_cores(list(cores))
 
 
+def reconstruct_interleaved(cores: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Flat fp32 tensor in (i1,o1,...,id,od) order from cores (r_k, i_k, o_k, r_{k+1}): the chain of small-K matmuls
+    (tt.py:213-237) already produces this layout, which is also what the decomposition sweep consumes."""
+    c0 = cores[0]
+    if not c0.is_cuda:
+        raise SowB200Error("TensorTrain.reconstruct needs CUDA cores (sm_100a kernels only, no CPU fallback)")
+    res = c0.detach().to(torch.float32).reshape(-1, c0.shape[-1])
+    for c in cores[1:]:
+        cm = c.detach().to(torch.float32).reshape(c.shape[0], -1)
+        res = ops.matmul_rk(res, cm).reshape(-1, c.shape[-1])
+    return res.reshape(-1)
+
+
 def _reconstruct_cores(cores: Sequence[torch.Tensor]) -> torch.Tensor:
     """(i1..id, o1..od)-shaped fp32 tensor from cores (r_k, i_k, o_k, r_{k+1}) via the small-K matmul kernel."""
     c0 = cores[0]

@@ -18,7 +18,7 @@ def declared_symbols():
 def test_header_declares_the_expected_entry_points():
     names = declared_symbols()
     for must in ["sow_linear_fwd", "sow_linear_bwd_factors", "sow_linear_bwd_dx", "sow_merge_grouped", "sow_thin_qr",
-                 "tt_project", "tt_interleave", "tt_deinterleave", "tt_matmul_rk", "tt_gather2", "tt_project2", "tt_reconstruct2", "tt_adam_fused2", "tt_adam2_head", "tt_adam2_fused", "tt_adam2_workspace_bytes", "tt_adam2_step", "tt_adam_dense",
+                 "tt_project", "tt_interleave", "tt_deinterleave", "tt_matmul_rk", "tt_gather2", "tt_project2", "tt_reconstruct2", "tt_adam_fused2", "tt_adam2_head", "tt_adam2_fused", "tt_adam2_workspace_bytes", "tt_adam2_step", "tt_adam_interleaved", "tt_adam_dense",
                  "sow_adam_multi", "sow_workspace_bytes", "sow_last_error", "sow_abi_version"]:
         assert must in names, must
 
