@@ -15,6 +15,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
+def pytest_sessionstart(session):
+    """The C-ABI library is a build artefact (git-ignored): build it in-tree if this checkout does not have it yet."""
+    lib = os.path.join(ROOT, "sow_b200", "csrc", "libsow_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 class Golden:
     """Lazy view over tests/golden/<group>.npz with '/'-separated keys."""
 
