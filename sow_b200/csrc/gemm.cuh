@@ -6,13 +6,13 @@
 //   warp 0 / lane 0 : TMA producer  (global -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1 / lane 0 : MMA issuer    (tcgen05.mma, M=128 x N=BN x K=16, fp32 accumulators in TMEM, 2 stages)
 //   warp 2          : TMEM allocator / deallocator
-//   warps 4..7      : epilogue      (tcgen05.ld -> registers -> {bf16 via swizzled smem + TMA store | fp32 red.add})
+//   warps 4..7      : epilogue      (tcgen05.ld -> registers -> {bf16 via swizzled smem + TMA store | fp32 split-K partial})
 //
 // Operand "majorness" is a template parameter because the SoW hot path needs all four combinations without
 // re-laying-out any user-visible tensor (reference layout of W is (in,out), tn_gradient/layer/sow.py:28,74-79):
 //   forward   y  = x.W      : A K-major,  B MN-major  (W rows are K, N contiguous)
 //   backward  dX = dY.W^T   : A K-major,  B K-major   (same W buffer, rows are N, K contiguous)
-//   backward  dA = x^T.dt   : A MN-major, B MN-major  (split-K over tokens, fp32 red.add epilogue)
+//   backward  dA = x^T.dt   : A MN-major, B MN-major  (split-K over tokens, fp32 partials summed in a fixed order)
 // The optional second operand pair (A2,B2) is the rank-r "tail": extra 64-deep k-blocks appended to the same
 // accumulator, which is how the low-rank term is fused into the base GEMM (no second pass over y / dX).
 #pragma once
@@ -30,7 +30,7 @@ constexpr int kStageCBytes = kBM * kStoreBoxCols * 2;              // 16 KB per 
 
 enum EpiMode : int {
   EPI_BF16_TMA = 0,    // D -> bf16, via smem staging + TMA store (clips M/N tails)
-  EPI_F32_ATOMIC = 1,  // D -> fp32 PARTIAL of split s stored at out_f32[s*split_stride + row*ldc + col]; the caller sums the
+  EPI_F32_PARTIAL = 1,  // D -> fp32 PARTIAL of split s stored at out_f32[s*split_stride + row*ldc + col]; the caller sums the
                        // splits in a fixed order (bit-reproducible, unlike red.global.add; no zero-fill needed)
 };
 
@@ -42,8 +42,8 @@ struct GemmParams {
   int kb_per_split;
   float alpha;
   const __nv_bfloat16* bias;  // nullable, length N (EPI_BF16_TMA only)
-  float* out_f32;             // EPI_F32_ATOMIC only
-  int64_t split_stride;       // EPI_F32_ATOMIC only: elements between the partial outputs of consecutive splits
+  float* out_f32;             // EPI_F32_PARTIAL only
+  int64_t split_stride;       // EPI_F32_PARTIAL only: elements between the partial outputs of consecutive splits
   int ldc;
 };
 

@@ -156,7 +156,7 @@ static int launch_gemm(const Operand& A, const Operand& B, const Operand* A2, co
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-// number of split-K partials launch_gemm<64, ..., EPI_F32_ATOMIC> produces for an [M x 64] output contracted over K
+// number of split-K partials launch_gemm<64, ..., EPI_F32_PARTIAL> produces for an [M x 64] output contracted over K
 static int splitk_count(int M, int K) {
   const int tiles = ceil_div(M, kBM), kb_total = ceil_div(K, kBK);
   int splits = num_sms() / std::max(1, tiles);
@@ -270,14 +270,14 @@ int sow_linear_bwd_factors(const void* dy, const void* x, const void* t, const v
   if (rc) return rc;
   // dB^T [out, r_pad] = dY^T . t   (both operands MN-major; K = T, split-K into fp32 partials summed by finalize)
   Operand opT{t, uint64_t(T), uint64_t(r_pad), uint64_t(r_pad)};
-  rc = launch_gemm<64, true, true, EPI_F32_ATOMIC>(opDY, opT, nullptr, nullptr, nullptr, partB, r_pad, out, r_pad,
+  rc = launch_gemm<64, true, true, EPI_F32_PARTIAL>(opDY, opT, nullptr, nullptr, nullptr, partB, r_pad, out, r_pad,
                                                    static_cast<int>(T), 0, 1.0f, nullptr, true, stream, PROF_GEMM_SPLITK,
                                                    &splitsB);
   if (rc) return rc;
   // dA [in, r_pad] = x^T . dt
   Operand opX{x, uint64_t(T), uint64_t(in), uint64_t(in)};
   Operand opDT{dt, uint64_t(T), uint64_t(r_pad), uint64_t(r_pad)};
-  rc = launch_gemm<64, true, true, EPI_F32_ATOMIC>(opX, opDT, nullptr, nullptr, nullptr, partA, r_pad, in, r_pad,
+  rc = launch_gemm<64, true, true, EPI_F32_PARTIAL>(opX, opDT, nullptr, nullptr, nullptr, partA, r_pad, in, r_pad,
                                                    static_cast<int>(T), 0, 1.0f, nullptr, true, stream, PROF_GEMM_SPLITK,
                                                    &splitsA);
   if (rc) return rc;
