@@ -104,25 +104,86 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+SHAPES = {   # scripts/configs/*.json of the reference (data): hidden, intermediate, layers
+    "llama_9m": (128, 352, 4), "llama_60m": (512, 1376, 8), "llama_130m": (768, 2048, 12),
+    "llama_350m": (1024, 2736, 24), "llama_7b": (4096, 11008, 32), "roberta_base": (768, 3072, 12),
+}
+
+
+def workload_name(args):
+    h, ff, L = SHAPES[args.model]
+    if args.model.startswith("roberta"):
+        kind = "GLUE-shaped fine-tuning (sequence classification, synthetic labels, mode keep, frozen base)"
+    elif args.mode == "pretrain":
+        kind = "pre-training"
+    else:
+        kind = "fine-tuning (mode keep, frozen base" + (", activation checkpointing" if args.act_ckpt else "") + ")"
+    return (f"{args.model} (h={h}, ff={ff}, L={L}) SoW rank {args.rank} {kind}, seq {args.seq}, steady state after 1 merge "
+            f"(dense W), fwd+bwd+grad-avg+AdamW per step")
+
+
+def run_ref_subprocess(extra, timeout=1500):
+    """Run baseline/ref_runner.py (the unmodified reference from baseline/_ref, own interpreter because its package is
+    also called tn_gradient) and return its JSON line, or None when baseline/_ref is absent or the run failed."""
+    runner = os.path.join(ROOT, "baseline", "ref_runner.py")
+    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "tn_gradient", "layer", "sow.py")):
+        return None
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        res = subprocess.run([sys.executable, runner] + [str(a) for a in extra], capture_output=True, text=True,
+                             timeout=timeout, env=env, cwd=os.path.join(ROOT, "baseline"))
+    except Exception:
+        return None
+    for ln in reversed(res.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            try:
+                return json.loads(ln)
+            except ValueError:
+                pass
+    sys.stderr.write("[bench] reference runner failed:\n" + res.stderr[-2000:] + "\n")
+    return None
+
+
+def ref_workload_args(args):
+    """Same workload for the reference arm as for ours (model, rank, seq, mode, scale, optimizer hyper-parameters)."""
+    if args.model.startswith("roberta"):
+        return ["--model", args.model, "--rank", args.rank, "--seq", args.seq, "--mode", "keep", "--scale", 1.0,
+                "--lr", 5e-5, "--sow-lr", 1.2e-4]
+    return ["--model", args.model, "--rank", args.rank, "--seq", args.seq, "--mode", args.mode,
+            "--scale", 1.0 if args.mode == "pretrain" else 0.125]
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure Python
-    and /root/reference does not exist on the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, all host threads.
+    Drives the UNMODIFIED reference package (baseline/_ref: stock tn_gradient.prepare.prepare_sow / SoWLinear /
+    accumulate, installed by baseline/install_ref.sh) in the loop order of scripts/simple_train.py:596-650; falls
+    back to the oracle port (oracle/cpu_trainer.py) only when baseline/_ref is absent.  Each step is a bounded
+    sample of the workload (2 sequences instead of the per-GPU batch) so that the run ends within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.cpu_trainer import time_cpu_training
     sample_batch = 2
     t0 = time.time()
-    res = time_cpu_training(args.model, args.rank, batch=sample_batch, seq_len=args.seq, steps=args.steps,
-                            warmup=max(1, args.warmup))
+    W = max(1, args.warmup)
+    res = run_ref_subprocess(ref_workload_args(args) + ["--batch", sample_batch, "--steps", args.steps, "--warmup", W,
+                                                        "--device", "cpu", "--dtype", "f32", "--merge-at", 0])
+    kind = "reference"
+    if res is None:
+        from oracle.cpu_trainer import time_cpu_training
+        res = time_cpu_training(args.model, args.rank, batch=sample_batch, seq_len=args.seq, steps=args.steps, warmup=W)
+        kind = "port"
     line = {
         "impl": "reference", "metric": "train_tokens_per_s", "value": res["tokens_per_s"], "unit": "tokens/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, args.warmup),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
         "ms_per_step": res["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} SoW r={args.rank} pre-training step, seq {args.seq}, steady state after 1 merge",
-                   "sample": f"{sample_batch} x {args.seq} tokens per step on host cores (fp32, eager torch ops of the reference)"},
-        "cpu_baseline": {"value": res["tokens_per_s"], "unit": "tokens/s", "cores": res["threads"], "kind": "port",
+        "config": {"workload": workload_name(args),
+                   "sample": f"{sample_batch} x {args.seq} tokens per step on host cores (fp32, the reference's stock "
+                             f"SoWLinear / prepare_sow / accumulate from baseline/_ref)" if kind == "reference" else
+                             f"{sample_batch} x {args.seq} tokens per step on host cores (fp32, oracle port)"},
+        "cpu_baseline": {"value": res["tokens_per_s"], "unit": "tokens/s", "cores": res["threads"], "kind": kind,
                          "sample": f"{args.steps} steps of {sample_batch}x{args.seq} tokens, merge in warm-up"},
         "e2e": {"value": res["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
@@ -337,16 +398,12 @@ def main():
                      "speedup_of_this_build": value / res["tokens_per_s"]}
 
     if rank == 0:
-        shp = LLAMA_SHAPES[args.model]
         line = {
             "metric": "train_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": f"{args.model} (h={shp['hidden_size']}, ff={shp['intermediate_size']}, L={shp['num_hidden_layers']}) "
-                            f"SoW rank {args.rank} bf16 " + ("pre-training" if args.mode == "pretrain" else "fine-tuning (mode keep, frozen base"
-                            + (", activation checkpointing" if args.act_ckpt else "") + ")") + ", steady state after 1 merge (dense W), "
-                            f"fwd+bwd+grad-avg+fused AdamW per step",
+                "workload": workload_name(args),
                 "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "tokens_per_step": tokens_per_step,
                 "parallelism": f"dp{world}", "l2": "working set per step (>1 GB weights+activations) exceeds the 126 MB L2; no flush needed",
                 "optimizer": "FusedAdamW (sow_adam_multi)" if cfg.fused_optimizer else "torch.optim.AdamW",

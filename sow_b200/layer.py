@@ -259,9 +259,15 @@ def _merge_dense(mods: List[SoWLinear]) -> None:
         pdtype = A.dtype
         A_c, B_c = _bf16c(A), _bf16c(B)
         W_old = mod.acc_downweight
-        if W_old.numel() != 0 and mod.acc_upweight.numel() != 0:
-            # last QR-growth step reached full rank: expand the factored accumulation once (sow.py:137-138)
-            W_old = (W_old.detach() @ mod.acc_upweight.detach())
+        expanded = W_old.numel() != 0 and mod.acc_upweight.numel() != 0
+        if expanded:
+            # last QR-growth step reached full rank: expand the factored accumulation once (sow.py:137-138); the
+            # product is a temporary, so the merged result must be bound as the new acc_downweight below
+            tgt = W_old.dtype
+            W_tmp = _bf16c((W_old.detach() @ mod.acc_upweight.detach()).to(dev))
+            items.append((W_tmp, W_tmp, A_c, B_c, mod.scale))
+            post.append((mod, W_tmp, tgt))
+            continue
         has_prev = W_old.numel() != 0
         if has_prev and W_old.dtype == torch.bfloat16 and W_old.is_contiguous() and W_old.device == dev:
             items.append((W_old.data, W_old.data, A_c, B_c, mod.scale))      # in-place RMW: pointer stays stable

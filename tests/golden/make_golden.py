@@ -180,6 +180,7 @@ def make_merge_cases(ref_sow, out):
         ("dense_bf16", 128, 192, 50, 1, 1.0, torch.bfloat16, True),
         ("dense_niter2_f32", 32, 40, 4, 2, 0.25, torch.float32, True),
         ("factored_f32", 64, 48, 10, 2, 1.0, torch.float32, False),
+        ("factored_bf16", 64, 48, 10, 2, 1.0, torch.bfloat16, False),   # crosses the full-rank boundary in bf16
     ]:
         torch.manual_seed(77)
         layer = ref_sow.SoWLinear(fin, fout, bias=False, rank=r, n_iter=n_iter, scale=scale, init_method="normal",

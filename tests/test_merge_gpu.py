@@ -15,7 +15,7 @@ def _mk(fin, fout, r, n_iter, scale, dtype, init="normal"):
     return SoWLinear(fin, fout, bias=False, rank=r, n_iter=n_iter, scale=scale, init_method=init, dtype=dtype, device="cuda")
 
 
-@pytest.mark.parametrize("case", ["dense_f32", "dense_bf16", "dense_niter2_f32", "factored_f32"])
+@pytest.mark.parametrize("case", ["dense_f32", "dense_bf16", "dense_niter2_f32", "factored_f32", "factored_bf16"])
 def test_merge_matches_reference_golden(golden_merge, case):
     g = golden_merge
     fin, fout, r, n_iter = [int(v) for v in g[f"merge/{case}/meta"]]
@@ -42,10 +42,11 @@ def test_merge_matches_reference_golden(golden_merge, case):
         if g[p + "Wup"].size == 0:
             assert layer.acc_upweight.numel() == 0
             assert rel_err(Wd, g[p + "W"]) < 1e-2           # bf16 compute policy, fp32 accumulate
+            assert float(np.abs(Wd).max()) > 0                # the merged update was kept (not written to a dropped temporary)
         else:
             Wu = layer.acc_upweight.float().cpu().numpy()
             assert Wd.shape == g[p + "W"].shape and Wu.shape == g[p + "Wup"].shape
-            assert rel_err(Wd @ Wu, g[p + "W"].astype(np.float64) @ g[p + "Wup"].astype(np.float64)) < 1e-4
+            assert rel_err(Wd @ Wu, g[p + "W"].astype(np.float64) @ g[p + "Wup"].astype(np.float64)) < (3e-2 if "bf16" in case else 1e-4)
         # factor re-init: B zero, A ~ N(0, .02) here (init_method "normal"), Parameter identity preserved
         assert [id(q) for q in list(layer.downscale_weights) + list(layer.upscale_weights)] == ids
         for B in layer.upscale_weights:

@@ -34,7 +34,7 @@ def test_linear_forward_backward_matches_reference(golden_linear, case):
         assert rel_err(dbias, g[p + "dbias"]) < tol
 
 
-@pytest.mark.parametrize("case", ["dense_f32", "dense_bf16", "dense_niter2_f32", "factored_f32"])
+@pytest.mark.parametrize("case", ["dense_f32", "dense_bf16", "dense_niter2_f32", "factored_f32", "factored_bf16"])
 def test_merge_matches_reference(golden_merge, case):
     g = golden_merge
     fin, fout, r, n_iter = [int(v) for v in g[f"merge/{case}/meta"]]
@@ -55,8 +55,9 @@ def test_merge_matches_reference(golden_merge, case):
         else:
             # factored branch: Q, R individually (same LAPACK Householder convention) and their product
             assert W.shape == g[p + "W"].shape and Wup.shape == g[p + "Wup"].shape
-            assert rel_err(W @ Wup, g[p + "W"].astype(np.float64) @ g[p + "Wup"].astype(np.float64)) < tol
-            assert rel_err(W, g[p + "W"]) < 1e-4
+            # (bf16: the reference stores Q and R rounded to bf16, the oracle keeps them in fp64)
+            assert rel_err(W @ Wup, g[p + "W"].astype(np.float64) @ g[p + "Wup"].astype(np.float64)) < (3e-2 if "bf16" in case else tol)
+            assert rel_err(W, g[p + "W"]) < (3e-2 if "bf16" in case else 1e-4)
 
 
 def test_reinit_normal_qr_matches_reference(golden_merge):
