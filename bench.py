@@ -43,6 +43,15 @@ def parse_args():
     return ap.parse_args()
 
 
+def load_traffic():
+    """ncu-measured DRAM bytes per launch of the kernels the roofline names, with the profiles/ file they come from."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -208,8 +217,6 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
@@ -291,14 +298,20 @@ def main():
     # (simple_train.py:618-626) the merge is issued right behind a backward pass, with no host synchronisation in
     # between, so the GPU is at its working clocks.  After the first merge B = 0, so repeated merges leave W unchanged
     # numerically while moving exactly the same bytes.
-    merge_ms = []
+    merge_ms, merge_event_ms, merge_event_wall_ms = [], [], []
     mg_bytes = 0.0
     for i in range(5):
         torch.cuda.synchronize()
         ops.profile_enable(True)
         trainer.step(dev_batches[i % n_batches])
-        trainer.merge()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw = time.perf_counter()
+        m0.record()
+        trainer.merge()               # accumulate(model) + reset_optimizer: merge kernel, thin-QR re-init, broadcast of A_new
+        m1.record()
         torch.cuda.synchronize()
+        merge_event_wall_ms.append((time.perf_counter() - tw) * 1e3)
+        merge_event_ms.append(m0.elapsed_time(m1))
         ms_i, mg_bytes, mg_n = ops.profile_read("merge")
         ops.profile_enable(False)
         merge_ms.append(ms_i)
@@ -344,34 +357,50 @@ def main():
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"]
     step_ms = ms_max / K
+    traffic = load_traffic()
     roofline = {
-        "kernel": "sow_gemm_kernel<BN=256> (y = x.W + t.B and dX = dY.W^T + dt.A^T, tcgen05/TMEM/TMA)",
+        "kernel": "sow_gemm_kernel<BN=256> (y_i = x.W_i + t_i.B_i and the group dX = sum_i dY_i.W_i^T + dt_cat.A_cat^T, "
+                  "tcgen05/TMEM/TMA)",
         "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf if peak_tf else None,
-        # dram__bytes_read + dram__bytes_write of ONE launch from the committed ncu --set full capture
-        # (profiles/r01_gemm_v2_ncu_full_summary.csv, forward launch of the gate/up shape T=16384, 1024->2736, r=50;
-        # algorithmic bytes of that launch: x 33.6 + W 5.6 + y 89.7 + t,B 2.4 = 131 MB -- part of y is still dirty in L2)
-        "traffic": 82.16e6, "traffic_unit": "bytes/launch (ncu, gate/up forward at T=16384)",
+        "frac_of_burst_peak": achieved_tf / peaks["bf16_tflops"] if peaks["bf16_tflops"] else None,
+        "flops_accounting": "algorithmic, un-padded rank (SURVEY.md 8d)",
+        # dram__bytes_read + dram__bytes_write of ONE forward launch at the bench shape, from the committed ncu --set full
+        # capture named in profiles/r02_traffic.json (null until that capture exists for this shape)
+        "traffic": traffic.get("gemm_fwd", {}).get("bytes") if B * S == traffic.get("gemm_fwd", {}).get("T") else None,
+        "traffic_source": traffic.get("gemm_fwd", {}).get("source"),
         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
         "launches_timed": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
         "share_of_step": (gemm_ms / max(args.profile_steps, 1)) / step_ms,
+        "share_of_step_fwd": (kern["gemm_fwd"]["ms_total"] / max(args.profile_steps, 1)) / step_ms,
+        "share_of_step_dx": (kern["gemm_dx"]["ms_total"] / max(args.profile_steps, 1)) / step_ms,
     }
     merge_gbs = mg_bytes / (mg_ms / 1e3) / 1e9 if mg_ms > 0 else 0.0
     extra_kernels = {
         "merge": {"bound": "hbm", "achieved": merge_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                   "frac": merge_gbs / peaks["hbm_gbs"], "ms": mg_ms, "algorithmic_bytes": mg_bytes, "launches": mg_n,
                   "events": len(merge_ms), "ms_all": merge_ms,
-                  # dram__bytes_read + dram__bytes_write of one launch, ncu --set full (profiles/r01_merge_v3_ncu_full_summary.csv:
-                  # 729 MB + 553 MB; the rest of the written data is still dirty in L2 when the kernel ends)
-                  "traffic": 1.282e9 if abs(mg_bytes - 1256265216.0) < 1 else None},
+                  # whole merge EVENT as the training loop sees it (simple_train.py:618-626): grouped merge kernel + thin-QR
+                  # re-initialisation of every A + zeroing of B + broadcast of A_new + reset_optimizer; CUDA events / host wall
+                  "merge_event_ms": statistics.median(merge_event_ms),
+                  "merge_event_wall_ms": statistics.median(merge_event_wall_ms),
+                  "traffic": traffic.get("merge", {}).get("bytes") if abs(mg_bytes - traffic.get("merge", {}).get("algorithmic_bytes", -1)) < 1 else None,
+                  "traffic_source": traffic.get("merge", {}).get("source")},
     }
     extra_kernels.update(tt_rows)
-    for k in ("gemm_skinny", "gemm_splitk", "adam"):
+    for k in ("gemm_skinny", "gemm_splitk", "gemm_k2", "adam"):
         d = kern[k]
         if d["ms_total"] > 0:
             rate = d["work"] / (d["ms_total"] / 1e3)
             extra_kernels[k] = {"ms_per_step": d["ms_total"] / args.profile_steps, "launches_per_step": d["launches"] / args.profile_steps,
                                 "achieved": rate / (1e9 if k == "adam" else 1e12), "unit": "GB/s" if k == "adam" else "TFLOP/s"}
+    side = sum(kern[k]["ms_total"] for k in ("gemm_skinny", "gemm_splitk", "gemm_k2")) / args.profile_steps
+    extra_kernels["rank_r_side_path_ms_per_step"] = side          # t_cat + dA_cat + fused dt/dB (round 1: 16.7 ms + pack/finalize)
+    fam_ms = gemm_ms + sum(kern[k]["ms_total"] for k in ("gemm_skinny", "gemm_splitk", "gemm_k2"))
+    fam_fl = gemm_flops + sum(kern[k]["work"] for k in ("gemm_skinny", "gemm_splitk", "gemm_k2"))
+    extra_kernels["sow_gemm_family"] = {"achieved": fam_fl / (fam_ms / 1e3) / 1e12 if fam_ms > 0 else 0.0, "unit": "TFLOP/s",
+                                        "frac_of_sustained": fam_fl / (fam_ms / 1e3) / 1e12 / peak_tf if fam_ms > 0 else None,
+                                        "ms_per_step": fam_ms / args.profile_steps}
     extra_kernels["gemm_fwd_ms_per_step"] = kern["gemm_fwd"]["ms_total"] / args.profile_steps
     extra_kernels["gemm_dx_ms_per_step"] = kern["gemm_dx"]["ms_total"] / args.profile_steps
 

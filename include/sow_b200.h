@@ -51,43 +51,59 @@ const char* sow_last_error(void);
  * Live per-kernel timing for bench.py's roofline: while enabled, every launch of the classes below is bracketed
  * by CUDA events on the launching stream.  sow_profile_read sums elapsed milliseconds, algorithmic work (flops for
  * GEMM classes, bytes for merge / Adam) and the launch count of one class.  Classes: 0 forward GEMM (y), 1 dX GEMM,
- * 2 skinny GEMMs (t, dt), 3 split-K GEMMs (dA, dB), 4 grouped merge, 5 multi-tensor Adam.
+ * 2 skinny GEMM (t_cat), 3 split-K GEMM (dA_cat), 4 grouped merge, 5 multi-tensor Adam, 6 fused dt + dB pass.
  */
 int sow_profile_enable(int on);
 int sow_profile_read(int klass, double* total_ms, double* total_work, int64_t* launches);
-
-/* Bytes of scratch the op needs for the given problem (T tokens, in/out features, rank r). */
-size_t sow_workspace_bytes(int op, int64_t T, int in, int out, int r);
 
 /* Rank padded to the k-block granularity used for the staged low-rank activations t / dt ([T, r_pad] bf16). */
 int sow_rank_pad(int r);
 
 /*
- * SoW linear forward.   Replaces SoWLinear.forward, tn_gradient/layer/sow.py:107-126
- *     y[T,out] = x[T,in] . W[in,out]  +  scale * (x . A[in,r]) . B[r,out]  (+ bias[out])
- * W may be NULL (pre-merge phase: acc_downweight is empty, sow.py:69-70) -> rank-r term only.
- * t_out[T, r_pad] (bf16) receives scale * x . A, the tensor autograd saves for backward.
+ * One projection of a GROUP of SoW linears that read the same input x[T,in] (q/k/v or gate/up of a transformer block;
+ * a lone projection is a group of one).  All matrices bf16 row-major.  Members may differ in `out`, `r` and `scale`.
  */
-int sow_linear_fwd(const void* x, const void* W, const void* A, const void* B, const void* bias, void* y,
-                   void* t_out, int64_t T, int in, int out, int r, float scale, int dtype, void* ws,
-                   size_t ws_bytes, void* stream);
+typedef struct sowb_group_member {
+  const void* W;    /* (in,out) frozen accumulation acc_downweight, or NULL before the first merge (sow.py:69-70) */
+  const void* A;    /* (in,r)   downscale_weights[i]                                                              */
+  const void* B;    /* (r,out)  upscale_weights[i]                                                                */
+  const void* bias; /* (out) or NULL                                              [forward]                      */
+  void* y;          /* (T,out) output                                             [forward]                      */
+  const void* dy;   /* (T,out) upstream gradient                                  [backward]                     */
+  void* dA;         /* (in,r)  gradient of A, or NULL                             [backward]                     */
+  void* dB;         /* (r,out) gradient of B, or NULL                             [backward]                     */
+  void* dbias;      /* (out)   gradient of bias, or NULL                          [backward]                     */
+  int out, r;
+  float scale;
+} sowb_group_member;
+
+/* Bytes of scratch sow_group_bwd needs (op = SOWB_OP_LINEAR_BWD; the forward needs none). */
+size_t sow_group_workspace_bytes(int op, int64_t T, int in, const sowb_group_member* members_host, int n);
 
 /*
- * Factor gradients.   Replaces the MmBackward nodes autograd records at sow.py:117,119:
- *     dt[T,r_pad] = scale * dY . B^T          dB[r,out] = t^T . dY          dA[in,r] = x^T . dt
- * (t is the tensor saved by sow_linear_fwd, which already carries `scale`).  dbias[out] = sum_T dY if non-NULL.
- * The full in x out weight gradient is never formed (W is frozen: sow.py:69-70, prepare.py:142,150).
+ * Forward of a group.   Replaces SoWLinear.forward, tn_gradient/layer/sow.py:107-126, for every member i:
+ *     y_i[T,out_i] = x[T,in] . W_i[in,out_i]  +  scale_i * (x . A_i[in,r_i]) . B_i[r_i,out_i]  (+ bias_i)
+ * in 2 + n launches: the factors are packed into A_cat[in,R] = [A_0|0|A_1|0|...] (each member zero-padded to
+ * sow_rank_pad(r_i) columns, R = their sum), ONE skinny GEMM computes t_cat[T,R] = scale_i * x . A_cat for all members
+ * (x is read once instead of n times), and each y_i is one tcgen05 GEMM with the t_i . B_i product fused in as an extra
+ * K-segment.  A_cat and t_cat (caller-allocated bf16) are what autograd saves for sow_group_bwd.
+ * W_i may be NULL (pre-merge phase) -> rank-r term only.  1 <= n <= 4.
  */
-int sow_linear_bwd_factors(const void* dy, const void* x, const void* t, const void* B, void* dt, void* dA,
-                           void* dB, void* dbias, int64_t T, int in, int out, int r, float scale, int dtype,
-                           void* ws, size_t ws_bytes, void* stream);
+int sow_group_fwd(const void* x, const sowb_group_member* members_host, int n, void* A_cat, void* t_cat, int64_t T,
+                  int in, int dtype, void* stream);
 
 /*
- * Input gradient.   Replaces MmBackward of sow.py:112 and :117:
- *     dX[T,in] = dY . W^T + dt . A^T          (W may be NULL -> second term only)
+ * Backward of a group.   Replaces the MmBackward nodes autograd records at sow.py:112,117,119 for every member:
+ *     dt_i = scale_i * dY_i . B_i^T        dB_i = t_i^T . dY_i        (ONE pass over dY_i produces both)
+ *     dA_cat = x^T . dt_cat                (ONE split-K GEMM for all members; x is read once)
+ *     dX = sum_i dY_i . W_i^T + dt_cat . A_cat^T      (ONE GEMM with K-concatenated segments; NULL dx skips it)
+ *     dbias_i = sum_T dY_i                 (if non-NULL)
+ * The full in x out weight gradient is never formed (W is frozen: sow.py:69-70, prepare.py:142,150).  All reductions
+ * across CTAs go through fp32 partials summed in a fixed order: results are bit-reproducible run to run.
+ * dt_cat[T,R] bf16 is caller-allocated scratch.  At most 3 members may carry a dense W.
  */
-int sow_linear_bwd_dx(const void* dy, const void* dt, const void* W, const void* A, void* dx, int64_t T, int in,
-                      int out, int r, int dtype, void* ws, size_t ws_bytes, void* stream);
+int sow_group_bwd(const void* x, const void* A_cat, const void* t_cat, const sowb_group_member* members_host, int n,
+                  void* dt_cat, void* dx, int64_t T, int in, int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /*
  * One entry of the grouped merge table (host memory, copied by the call).

@@ -39,6 +39,24 @@ class MergeEntry(ctypes.Structure):
     ]
 
 
+class GroupMember(ctypes.Structure):
+    """sowb_group_member (include/sow_b200.h)."""
+    _fields_ = [
+        ("W", ctypes.c_void_p),
+        ("A", ctypes.c_void_p),
+        ("B", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
+        ("y", ctypes.c_void_p),
+        ("dy", ctypes.c_void_p),
+        ("dA", ctypes.c_void_p),
+        ("dB", ctypes.c_void_p),
+        ("dbias", ctypes.c_void_p),
+        ("out_features", ctypes.c_int),
+        ("r", ctypes.c_int),
+        ("scale", ctypes.c_float),
+    ]
+
+
 _vp, _i, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
 _d = ctypes.c_double
 
@@ -48,11 +66,10 @@ SIGNATURES = {
     "sow_last_error": (ctypes.c_char_p, []),
     "sow_profile_enable": (_i, [_i]),
     "sow_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
-    "sow_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),
     "sow_rank_pad": (_i, [_i]),
-    "sow_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
-    "sow_linear_bwd_factors": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
-    "sow_linear_bwd_dx": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "sow_group_workspace_bytes": (_sz, [_i, _i64, _i, ctypes.POINTER(GroupMember), _i]),
+    "sow_group_fwd": (_i, [_vp, ctypes.POINTER(GroupMember), _i, _vp, _vp, _i64, _i, _i, _vp]),
+    "sow_group_bwd": (_i, [_vp, _vp, _vp, ctypes.POINTER(GroupMember), _i, _vp, _vp, _i64, _i, _i, _vp, _sz, _vp]),
     "sow_merge_table_stride": (_sz, []),
     "sow_merge_grouped": (_i, [ctypes.POINTER(MergeEntry), _i, _i, _vp, _sz, _vp]),
     "sow_thin_qr": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp, _sz, _vp]),

@@ -255,6 +255,6 @@ int sow_profile_read(int klass, double* total_ms, double* total_work, int64_t* l
   if (launches) *launches = n;
   return SOWB_OK;
 }
-int sow_abi_version(void) { return 1; }
+int sow_abi_version(void) { return 2; }
 const char* sow_last_error(void) { return sowb::g_err; }
 }

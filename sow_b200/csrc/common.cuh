@@ -47,11 +47,12 @@ int make_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint6
 enum ProfClass : int {
   PROF_GEMM_FWD = 0,     // y  = x.W + t.B          (flops)
   PROF_GEMM_DX = 1,      // dX = dY.W^T + dt.A^T    (flops)
-  PROF_GEMM_SKINNY = 2,  // t = x.A, dt = dY.B^T    (flops)
-  PROF_GEMM_SPLITK = 3,  // dA, dB                  (flops)
+  PROF_GEMM_SKINNY = 2,  // t_cat = x.[A_q|A_k|..]  (flops)
+  PROF_GEMM_SPLITK = 3,  // dA_cat = x^T.dt_cat     (flops)
   PROF_MERGE = 4,        // grouped merge           (bytes)
   PROF_ADAM = 5,         // multi-tensor Adam       (bytes)
-  PROF_NUM = 6,
+  PROF_GEMM_K2 = 6,      // fused dt + dB pass over dY (flops)
+  PROF_NUM = 7,
 };
 bool profile_enabled();
 struct ProfileScope {

@@ -1,6 +1,6 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a.
 //
-//   D[M,N] (+)= alpha * ( A[M,K] * B[K,N]  +  A2[M,K2] * B2[K2,N] )  (+ bias[N])
+//   D[M,N] = alpha[n/64] * sum_s A_s[M,K_s] * B_s[K_s,N]  (+ bias[N])        s = 0 .. nseg-1 (<= 4 segments)
 //
 // One CTA per SM, 256 threads:
 //   warp 0 / lane 0 : TMA producer  (global -> 128B-swizzled smem ring, mbarrier complete_tx)
@@ -13,8 +13,14 @@
 //   forward   y  = x.W      : A K-major,  B MN-major  (W rows are K, N contiguous)
 //   backward  dX = dY.W^T   : A K-major,  B K-major   (same W buffer, rows are N, K contiguous)
 //   backward  dA = x^T.dt   : A MN-major, B MN-major  (split-K over tokens, fp32 partials summed in a fixed order)
-// The optional second operand pair (A2,B2) is the rank-r "tail": extra 64-deep k-blocks appended to the same
-// accumulator, which is how the low-rank term is fused into the base GEMM (no second pass over y / dX).
+// The contraction is a list of K-SEGMENTS, each with its own pair of tensor maps, accumulated into the same TMEM tile:
+//   * the rank-r "tail" (t.B in the forward, dt.A^T in dX) is one more segment, which is how the low-rank term is fused
+//     into the base GEMM (no second pass over y / dX);
+//   * projections that share their input (q/k/v, gate/up) share ONE dX launch: dX = sum_p dY_p.W_p^T + dt_cat.A_cat^T is
+//     a 4-segment contraction, so dX is written once instead of n times plus n-1 elementwise adds;
+//   * fp32 modules run as bf16x3: [x_hi | x_hi | x_lo].[W_hi ; W_lo ; W_hi] is a 3-segment contraction.
+// alpha is looked up per 64-wide column block so that one skinny launch t_cat = x.[A_q|A_k|A_v] can apply each
+// projection's own scale.
 #pragma once
 #include "ptx.cuh"
 
@@ -34,13 +40,23 @@ enum EpiMode : int {
                        // splits in a fixed order (bit-reproducible, unlike red.global.add; no zero-fill needed)
 };
 
+constexpr int kMaxSeg = 4;
+constexpr int kMaxAlphaBlocks = 16;   // per-64-column alpha table covers N <= 1024 (wider outputs use alpha[0])
+
+struct GemmMaps {
+  CUtensorMap a[kMaxSeg];
+  CUtensorMap b[kMaxSeg];
+  CUtensorMap c;
+};
+
 struct GemmParams {
   int M, N;
-  int kb_main;         // number of kBK-deep k-blocks taken from (A ,B )
-  int kb_tail;         // number of kBK-deep k-blocks taken from (A2,B2)
+  int nseg;
+  int kb_end[kMaxSeg];  // cumulative count of kBK-deep k-blocks after segment s
   int m_tiles, n_tiles, splits;
   int kb_per_split;
-  float alpha;
+  int alpha_blocks;     // 0: alpha[0] for every column; else alpha[(col / 64)]
+  float alpha[kMaxAlphaBlocks];
   const __nv_bfloat16* bias;  // nullable, length N (EPI_BF16_TMA only)
   float* out_f32;             // EPI_F32_PARTIAL only
   int64_t split_stride;       // EPI_F32_PARTIAL only: elements between the partial outputs of consecutive splits
@@ -53,7 +69,7 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // leave room for 2 staging buffers (32 KB) + barriers inside the 227 KB opt-in limit
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN >= 192) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kStagingBytes = 2 * kStageCBytes;
   static constexpr int kBarBytes = 256;
@@ -63,9 +79,7 @@ struct GemmSmem {
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment
@@ -83,13 +97,11 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (p.kb_tail > 0) {
-      tma_prefetch_desc(&tmA2);
-      tma_prefetch_desc(&tmB2);
+    for (int sg = 0; sg < p.nseg; ++sg) {
+      tma_prefetch_desc(&maps.a[sg]);
+      tma_prefetch_desc(&maps.b[sg]);
     }
-    if (EPI == EPI_BF16_TMA) tma_prefetch_desc(&tmC);
+    if (EPI == EPI_BF16_TMA) tma_prefetch_desc(&maps.c);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S::kStages; ++i) {
@@ -112,7 +124,7 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
-  const int kb_total = p.kb_main + p.kb_tail;
+  const int kb_total = p.kb_end[p.nseg - 1];
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -125,15 +137,17 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n0 = (tile % p.n_tiles) * BN;
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+      int seg = 0;
+      while (kb_begin >= p.kb_end[seg]) ++seg;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = ring + stage * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
         mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-        const bool tail = kb >= p.kb_main;
-        const CUtensorMap* ma = tail ? &tmA2 : &tmA;
-        const CUtensorMap* mb = tail ? &tmB2 : &tmB;
-        const int k0 = (tail ? kb - p.kb_main : kb) * kBK;
+        while (kb >= p.kb_end[seg]) ++seg;
+        const CUtensorMap* ma = &maps.a[seg];
+        const CUtensorMap* mb = &maps.b[seg];
+        const int k0 = (kb - (seg ? p.kb_end[seg - 1] : 0)) * kBK;
         if (A_MN) {
           // global [K rows, M contiguous]: two boxes of (64 M) x (64 K)
 #pragma unroll
@@ -218,6 +232,7 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int b = 0; b < BN / kStoreBoxCols; ++b) {
           if (n0 + b * kStoreBoxCols >= p.N) break;  // uniform across the CTA
           uint8_t* stg = staging + (boxes_issued & 1) * kStageCBytes;
+          const float alpha = p.alpha[p.alpha_blocks ? min(p.alpha_blocks - 1, (n0 >> 6) + b) : 0];
           if (boxes_issued >= 2) {
             if (et == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
             named_barrier_sync(1, kEpiThreads);
@@ -233,7 +248,7 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                f[j] = p.alpha * __uint_as_float(v[c * 8 + j]);
+                f[j] = alpha * __uint_as_float(v[c * 8 + j]);
                 if (p.bias != nullptr) {
                   const int col = colbase + c * 8 + j;
                   if (col < p.N) f[j] += __bfloat162float(p.bias[col]);
@@ -251,7 +266,7 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           fence_proxy_async_smem();
           named_barrier_sync(1, kEpiThreads);
           if (et == 0) {
-            tma_store_2d(&tmC, stg, n0 + b * kStoreBoxCols, m0);
+            tma_store_2d(&maps.c, stg, n0 + b * kStoreBoxCols, m0);
             tma_store_commit();
           }
           ++boxes_issued;
@@ -260,6 +275,7 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int row = m0 + row_in_tile;
         const int split = w % p.splits;
         float* part = p.out_f32 + static_cast<int64_t>(split) * p.split_stride;
+        const float alpha = p.alpha[0];
 #pragma unroll 1
         for (int c32 = 0; c32 < BN / 32; ++c32) {
           if (n0 + c32 * 32 >= p.N) break;
@@ -272,12 +288,12 @@ sow_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(dst + 4 * j) =
-                    make_float4(p.alpha * __uint_as_float(v[4 * j]), p.alpha * __uint_as_float(v[4 * j + 1]),
-                                p.alpha * __uint_as_float(v[4 * j + 2]), p.alpha * __uint_as_float(v[4 * j + 3]));
+                    make_float4(alpha * __uint_as_float(v[4 * j]), alpha * __uint_as_float(v[4 * j + 1]),
+                                alpha * __uint_as_float(v[4 * j + 2]), alpha * __uint_as_float(v[4 * j + 3]));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (n0 + c32 * 32 + j < p.N) dst[j] = p.alpha * __uint_as_float(v[j]);
+                if (n0 + c32 * 32 + j < p.N) dst[j] = alpha * __uint_as_float(v[j]);
             }
           }
         }

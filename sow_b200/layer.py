@@ -63,60 +63,173 @@ def _bf16c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t if t.is_contiguous() else t.contiguous()
 
 
-class _SoWLinearFn(torch.autograd.Function):
-    """y = x.W + scale*(x.A).B + bias with W frozen.  Saves x and t = scale*x.A (T x r_pad), never forms dW.
+def _grad_dst(param: Optional[torch.Tensor]):
+    """Where the kernels should write the gradient of a factor: the parameter's view into a flat gradient bucket
+    (``_sow_grad_view``, set by parallel.FlatGradSync) when the parameter has no gradient yet -- autograd's AccumulateGrad
+    then adopts the returned view as ``param.grad`` without a copy or an add -- else a fresh tensor."""
+    if param is None:
+        return True
+    view = getattr(param, "_sow_grad_view", None)
+    if view is not None and param.grad is None and view.dtype == torch.bfloat16:
+        return view
+    return True
 
-    Inputs of other dtypes follow the bf16 compute policy: cast to bf16 on the way in, results cast
-    back to the caller's dtype.  ``W_c`` is the bf16 compute copy of W (W itself when W is bf16)."""
+
+class _SoWGroupFn(torch.autograd.Function):
+    """y_i = x.W_i + scale_i*(x.A_i).B_i + bias_i for the n projections of a group that read the same x, W_i frozen.
+    Saves x, the packed factors A_cat and t_cat = scale_i*x.A_cat (T x R); never forms dW.
+
+    Positional inputs after ``scales``: for each member (W_c or None, A, B, bias or None).  Inputs of other dtypes follow
+    the bf16 compute policy: cast to bf16 on the way in, results cast back to the caller's dtype.  ``W_c`` is
+    the bf16 compute copy of W (W itself when W is bf16)."""
 
     @staticmethod
-    def forward(ctx, x, W_c, A, B, bias, scale):
+    def forward(ctx, x, scales, *params):
+        n = len(scales)
         out_dtype = x.dtype
-        fin = A.shape[0]
+        Ws, As, Bs, biases = params[0::4], params[1::4], params[2::4], params[3::4]
+        fin = As[0].shape[0]
         lead = x.shape[:-1]
+        ctx.n = n
+        ctx.meta = (out_dtype, [a.dtype for a in As], [b.dtype for b in Bs],
+                    [None if b is None else b.dtype for b in biases], lead, fin,
+                    [a.shape for a in As], [b.shape for b in Bs])
         if x.numel() == 0:                      # empty batch: nothing to launch (the reference returns an empty tensor too)
             ctx.empty = True
-            ctx.meta = (x.dtype, A, B, bias, lead, fin)
-            return x.new_zeros(*lead, B.shape[1])
+            return tuple(x.new_zeros(*lead, b.shape[1]) for b in Bs)
         ctx.empty = False
         x2 = _bf16c(x.reshape(-1, fin))
-        A_c, B_c, bias_c = _bf16c(A), _bf16c(B), _bf16c(bias)
-        y, t = ops.linear_fwd(x2, W_c, A_c, B_c, bias_c, scale)
-        ctx.save_for_backward(x2, t, W_c, A_c, B_c)
-        ctx.scale = float(scale)
-        ctx.meta = (out_dtype, A.dtype, B.dtype, None if bias is None else bias.dtype, lead, fin)
-        y = y.reshape(*lead, B.shape[1])
-        return y if out_dtype == torch.bfloat16 else y.to(out_dtype)
+        Wc = [_bf16c(w) for w in Ws]
+        Bc = [_bf16c(b) for b in Bs]
+        ys, A_cat, t_cat = ops.group_fwd(
+            x2, [(Wc[i], _bf16c(As[i]), Bc[i], _bf16c(biases[i]), scales[i]) for i in range(n)])
+        ctx.save_for_backward(x2, A_cat, t_cat, *Wc, *Bc)
+        ctx.scales = tuple(float(s) for s in scales)
+        # leaf factor Parameters: their gradients may be written straight into a flat bucket view
+        ctx.leaves = [(a if isinstance(a, nn.Parameter) else None, b if isinstance(b, nn.Parameter) else None)
+                      for a, b in zip(As, Bs)]
+        outs = []
+        for y, b in zip(ys, Bs):
+            y = y.reshape(*lead, b.shape[1])
+            outs.append(y if out_dtype == torch.bfloat16 else y.to(out_dtype))
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, *dys):
+        n = ctx.n
+        out_dtype, a_dts, b_dts, bias_dts, lead, fin, a_shapes, b_shapes = ctx.meta
+        need = ctx.needs_input_grad
+        need_x = need[0]
+        grads = [None, None]
         if ctx.empty:
-            _, A, B, bias, lead, fin = ctx.meta
-            need_x, _, need_A, need_B, need_bias, _ = ctx.needs_input_grad
-            return (dy.new_zeros(*lead, fin) if need_x else None, None, torch.zeros_like(A) if need_A else None,
-                    torch.zeros_like(B) if need_B else None,
-                    torch.zeros_like(bias) if (need_bias and bias is not None) else None, None)
-        x2, t, W_c, A_c, B_c = ctx.saved_tensors
-        out_dtype, a_dt, b_dt, bias_dt, lead, fin = ctx.meta
-        need_x, _, need_A, need_B, need_bias, _ = ctx.needs_input_grad
-        dy2 = _bf16c(dy.reshape(-1, dy.shape[-1]))
-        dt, dA, dB, dbias = ops.linear_bwd_factors(dy2, x2, t, B_c, ctx.scale, bool(need_bias), fin)
-        dx = None
-        if need_x:
-            dx = ops.linear_bwd_dx(dy2, dt, W_c, A_c).reshape(*lead, fin)
+            for i in range(n):
+                nW, nA, nB, nb = need[2 + 4 * i: 6 + 4 * i]
+                grads += [None,
+                          torch.zeros(a_shapes[i], dtype=a_dts[i], device=dys[0].device) if nA else None,
+                          torch.zeros(b_shapes[i], dtype=b_dts[i], device=dys[0].device) if nB else None,
+                          torch.zeros(b_shapes[i][1], dtype=bias_dts[i], device=dys[0].device) if (nb and bias_dts[i] is not None) else None]
+            grads[0] = dys[0].new_zeros(*lead, fin) if need_x else None
+            return tuple(grads)
+        saved = ctx.saved_tensors
+        x2, A_cat, t_cat = saved[0], saved[1], saved[2]
+        Wc, Bc = saved[3:3 + n], saved[3 + n:3 + 2 * n]
+        members = []
+        for i in range(n):
+            nW, nA, nB, nb = need[2 + 4 * i: 6 + 4 * i]
+            dy2 = _bf16c(dys[i].reshape(-1, dys[i].shape[-1]))
+            pa, pb = ctx.leaves[i]
+            dA_dst = (_grad_dst(pa) if a_dts[i] == torch.bfloat16 else True) if nA else None
+            dB_dst = (_grad_dst(pb) if b_dts[i] == torch.bfloat16 else True) if nB else None
+            members.append((Wc[i], Bc[i], dy2, ctx.scales[i], dA_dst, dB_dst, bool(nb) and bias_dts[i] is not None))
+        dx, dAs, dBs, dbs = ops.group_bwd(x2, A_cat, t_cat, members, bool(need_x))
+        if dx is not None:
+            dx = dx.reshape(*lead, fin)
             if out_dtype != torch.bfloat16:
                 dx = dx.to(out_dtype)
-        dA = dA.to(a_dt) if need_A else None
-        dB = dB.to(b_dt) if need_B else None
-        dbias = dbias.to(bias_dt) if need_bias else None
-        return dx, None, dA, dB, dbias, None
+        grads[0] = dx
+        for i in range(n):
+            dA, dB, db = dAs[i], dBs[i], dbs[i]
+            grads += [None,
+                      None if dA is None else (dA if a_dts[i] == torch.bfloat16 else dA.to(a_dts[i])),
+                      None if dB is None else (dB if b_dts[i] == torch.bfloat16 else dB.to(b_dts[i])),
+                      None if db is None else (db if bias_dts[i] == torch.bfloat16 else db.to(bias_dts[i]))]
+        return tuple(grads)
 
 
 @torch.compiler.disable
+def sow_linear_group(x, scales, params):
+    """Kernel-backed SoW projections sharing one input.  Opaque to torch.compile (scripts/finetune.py:486-487 compiles
+    the model): the C-ABI calls are not traceable, so dynamo breaks the graph here and runs this call eagerly."""
+    return _SoWGroupFn.apply(x, tuple(scales), *params)
+
+
 def sow_linear(x, W_c, A, B, bias, scale):
-    """Kernel-backed SoW linear.  Opaque to torch.compile (scripts/finetune.py:486-487 compiles the model): the C-ABI
-    calls are not traceable, so dynamo breaks the graph here and runs this call eagerly."""
-    return _SoWLinearFn.apply(x, W_c, A, B, bias, scale)
+    """One projection = a group of one."""
+    return sow_linear_group(x, (scale,), (W_c, A, B, bias))[0]
+
+
+class SharedInputGroup:
+    """SoW projections of one block that are called with the SAME input tensor (q/k/v, gate/up; SURVEY.md 8f-4:
+    simple_train.py:318 lists them as separate target modules).  The first member called with a new x runs the whole
+    group through ONE autograd node (one pass over x for all t_i and dA_i, one dX for all members) and parks the other
+    members' outputs; the siblings, called with the identical tensor object, pick theirs up.  User-visible parameters and
+    module call sites stay untouched.  If the siblings turn out to be called with different tensors the group switches
+    itself off (each member then runs as a group of one)."""
+
+    MAX_MISSES = 4
+
+    def __init__(self, members: Sequence["SoWLinear"]):
+        self.members = list(members)
+        self.index = {id(m): i for i, m in enumerate(self.members)}
+        self.cache = None            # (x, x._version, grad_mode, {member index: parked output})
+        self.misses = 0
+        self.enabled = True
+
+    def usable(self) -> bool:
+        ms = self.members
+        if not self.enabled or len(ms) < 2 or len(ms) > 4:
+            return False
+        m0 = ms[0]
+        n_dense = 0
+        for m in ms:
+            if (m.in_features != m0.in_features or m.acc_upweight.numel() != 0 or
+                    m.downscale_weights[0].device != m0.downscale_weights[0].device):
+                return False
+            n_dense += m.acc_downweight.numel() != 0
+        return n_dense <= 3
+
+    def forward(self, mod: "SoWLinear", x: torch.Tensor) -> torch.Tensor:
+        idx = self.index[id(mod)]
+        c = self.cache
+        if c is not None and c[0] is x and c[1] == x._version and c[2] == torch.is_grad_enabled() and idx in c[3]:
+            y = c[3].pop(idx)
+            if not c[3]:
+                self.cache = None
+            return y
+        if c is not None and c[3]:
+            self.misses += 1         # parked outputs were never picked up: the members do not share their input
+            if self.misses >= self.MAX_MISSES:
+                self.enabled = False
+                self.cache = None
+                return _forward_modules([mod], x)[0]
+        ys = _forward_modules(self.members, x)
+        self.cache = (x, x._version, torch.is_grad_enabled(), {i: y for i, y in enumerate(ys) if i != idx})
+        return ys[idx]
+
+
+def _forward_modules(mods: Sequence["SoWLinear"], x: torch.Tensor):
+    params, scales = [], []
+    for m in mods:
+        A_list, B_list = list(m.downscale_weights), list(m.upscale_weights)
+        if len(A_list) == 1:
+            A, B = A_list[0], B_list[0]
+        else:
+            # sum_i (x.A_i).B_i == (x.[A_1|..|A_n]).[B_1;..;B_n]: one fused call; autograd splits the grads
+            A = torch.cat(A_list, dim=1)
+            B = torch.cat(B_list, dim=0)
+        params += [m._compute_weight(), A, B, m.bias]
+        scales.append(m.scale)
+    return sow_linear_group(x, scales, params)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -176,6 +289,7 @@ class SoWLinear(nn.Module):
             self.register_parameter("bias", None)
         self._w_shadow = None       # bf16 compute copy of a non-bf16 acc_downweight
         self._w_shadow_key = None
+        self._group = None          # SharedInputGroup of the projections that read the same input (surgery.group_shared_inputs)
         if init_params:
             self.reset_parameters()
 
@@ -212,24 +326,22 @@ class SoWLinear(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise SowB200Error("SoWLinear.forward needs CUDA tensors (sm_100a kernels only, no CPU fallback)")
-        A_list = list(self.downscale_weights)
-        B_list = list(self.upscale_weights)
-        if len(A_list) == 1:
-            A, B = A_list[0], B_list[0]
-        else:
-            # sum_i (x.A_i).B_i == (x.[A_1|..|A_n]).[B_1;..;B_n]: one fused call; autograd splits the grads
-            A = torch.cat(A_list, dim=1)
-            B = torch.cat(B_list, dim=0)
         factored = self.acc_downweight.numel() != 0 and self.acc_upweight.numel() != 0
-        W_c = None if factored else self._compute_weight()
-        out = sow_linear(x, W_c, A, B, None if factored else self.bias, self.scale)
         if factored:
             # compat branch (direct construction with virtual_rank < min(in,out); never reached through
             # prepare_sow, prepare.py:120): the frozen factored accumulation goes through cuBLAS
+            A_list, B_list = list(self.downscale_weights), list(self.upscale_weights)
+            A = A_list[0] if len(A_list) == 1 else torch.cat(A_list, dim=1)
+            B = B_list[0] if len(B_list) == 1 else torch.cat(B_list, dim=0)
+            out = sow_linear(x, None, A, B, None, self.scale)
             out = out + (x @ self.acc_downweight.to(x.dtype)) @ self.acc_upweight.to(x.dtype)
             if self.bias is not None:
                 out = out + self.bias.to(out.dtype)
-        return out
+            return out
+        grp = self._group
+        if grp is not None and grp.usable():
+            return grp.forward(self, x)
+        return _forward_modules([self], x)[0]
 
     # ---- merge (sow.py:128-178) ---------------------------------------------------------------------------
     def accumulate(self) -> None:

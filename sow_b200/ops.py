@@ -71,59 +71,111 @@ def rank_pad(r: int) -> int:
 # SoW linear
 # ---------------------------------------------------------------------------------------------------------
 
-def linear_fwd(x: torch.Tensor, W: Optional[torch.Tensor], A: torch.Tensor, B: torch.Tensor,
-               bias: Optional[torch.Tensor], scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
-    """y = x.W + scale*(x.A).B (+bias);  x (T,in) bf16 contiguous.  Returns (y (T,out), t (T,r_pad))."""
-    _require_cuda(x, W, A, B, bias)
+def _check_bf16c(name: str, t: Optional[torch.Tensor]):
+    if t is not None and (t.dtype != torch.bfloat16 or not t.is_contiguous()):
+        raise SowB200Error(f"{name} must be a contiguous bf16 tensor")
+
+
+def group_fwd(x: torch.Tensor, members: Sequence[Tuple[Optional[torch.Tensor], torch.Tensor, torch.Tensor,
+                                                       Optional[torch.Tensor], float]]):
+    """Forward of a group of SoW projections that read the same x (T,in) bf16 contiguous (include/sow_b200.h:
+    sow_group_fwd).  members: (W (in,out) or None, A (in,r), B (r,out), bias or None, scale).
+    Returns ([y_i (T,out_i)], A_cat (in,R), t_cat (T,R)); A_cat / t_cat are what autograd saves for group_bwd."""
     lib = _lib.load()
+    n = len(members)
     T, fin = x.shape
-    r, fout = B.shape
-    rp = rank_pad(r)
-    y = torch.empty((T, fout), dtype=torch.bfloat16, device=x.device)
-    t = torch.empty((T, rp), dtype=torch.bfloat16, device=x.device)
-    nws = lib.sow_workspace_bytes(_lib.OP_LINEAR_FWD, T, fin, fout, r)
-    ws = workspace(x.device, nws)
-    rc = lib.sow_linear_fwd(_p(x), _p(W), _p(A), _p(B), _p(bias), _p(y), _p(t), T, fin, fout, r, float(scale),
-                            SOWB_BF16, _p(ws), ws.numel(), _stream_ptr(x.device))
-    check(rc, "sow_linear_fwd")
-    launch_counter["kernels"] += 3
-    return y, t
+    _require_cuda(x)
+    _check_bf16c("x", x)
+    arr = (_lib.GroupMember * n)()
+    ys = []
+    R = 0
+    for i, (W, A, B, bias, scale) in enumerate(members):
+        _require_cuda(W, A, B, bias)
+        for nm, t in (("W", W), ("A", A), ("B", B), ("bias", bias)):
+            _check_bf16c(nm, t)
+        r, fout = B.shape
+        if A.shape != (fin, r) or (W is not None and tuple(W.shape) != (fin, fout)):
+            raise SowB200Error("group_fwd: shape mismatch")
+        y = torch.empty((T, fout), dtype=torch.bfloat16, device=x.device)
+        ys.append(y)
+        arr[i].W, arr[i].A, arr[i].B, arr[i].bias = _p(W), _p(A), _p(B), _p(bias)
+        arr[i].y = _p(y)
+        arr[i].out_features, arr[i].r, arr[i].scale = fout, r, float(scale)
+        R += rank_pad(r)
+    A_cat = torch.empty((fin, R), dtype=torch.bfloat16, device=x.device)
+    t_cat = torch.empty((T, R), dtype=torch.bfloat16, device=x.device)
+    rc = lib.sow_group_fwd(_p(x), arr, n, _p(A_cat), _p(t_cat), T, fin, SOWB_BF16, _stream_ptr(x.device))
+    check(rc, "sow_group_fwd")
+    launch_counter["kernels"] += 2 + n
+    return ys, A_cat, t_cat
 
 
-def linear_bwd_factors(dy, x, t, B, scale: float, want_dbias: bool, fin: int):
-    """Returns (dt (T,r_pad), dA (in,r), dB (r,out), dbias or None)."""
-    _require_cuda(dy, x, t, B)
+def group_bwd(x: torch.Tensor, A_cat: torch.Tensor, t_cat: torch.Tensor, members, need_dx: bool):
+    """Backward of a group (sow_group_bwd).  members: (W or None, B (r,out), dy (T,out), scale, dA_dst, dB_dst,
+    want_dbias) where dA_dst / dB_dst are None (not needed), True (allocate) or a preallocated contiguous bf16 tensor of
+    the gradient's shape (e.g. a view into a flat gradient bucket) that the kernels write in place.
+    Returns (dx or None, [dA_i], [dB_i], [dbias_i])."""
     lib = _lib.load()
-    T, fout = dy.shape
-    r = B.shape[0]
-    rp = rank_pad(r)
-    dev = dy.device
-    dt = torch.empty((T, rp), dtype=torch.bfloat16, device=dev)
-    dA = torch.empty((fin, r), dtype=torch.bfloat16, device=dev)
-    dB = torch.empty((r, fout), dtype=torch.bfloat16, device=dev)
-    dbias = torch.empty((fout,), dtype=torch.bfloat16, device=dev) if want_dbias else None
-    nws = lib.sow_workspace_bytes(_lib.OP_LINEAR_BWD, T, fin, fout, r)
+    n = len(members)
+    T, fin = x.shape
+    dev = x.device
+    R = t_cat.shape[1]
+    arr = (_lib.GroupMember * n)()
+    dAs, dBs, dbs = [], [], []
+    keep = []
+    for i, (W, B, dy, scale, dA_dst, dB_dst, want_dbias) in enumerate(members):
+        _require_cuda(W, B, dy)
+        _check_bf16c("W", W)
+        _check_bf16c("B", B)
+        _check_bf16c("dy", dy)
+        r, fout = B.shape
+        if tuple(dy.shape) != (T, fout):
+            raise SowB200Error("group_bwd: dy shape mismatch")
+
+        def out_buf(dst, shape):
+            if dst is None:
+                return None
+            if dst is True:
+                return torch.empty(shape, dtype=torch.bfloat16, device=dev)
+            if tuple(dst.shape) != tuple(shape) or dst.dtype != torch.bfloat16 or not dst.is_contiguous() or dst.device != dev:
+                raise SowB200Error("group_bwd: gradient destination must be a contiguous bf16 tensor of the gradient's shape")
+            return dst.detach()          # fresh alias of the same memory: AccumulateGrad can adopt it as param.grad
+        dA = out_buf(dA_dst, (fin, r))
+        dB = out_buf(dB_dst, (r, fout))
+        db = torch.empty((fout,), dtype=torch.bfloat16, device=dev) if want_dbias else None
+        dAs.append(dA)
+        dBs.append(dB)
+        dbs.append(db)
+        arr[i].W, arr[i].B, arr[i].dy = _p(W), _p(B), _p(dy)
+        arr[i].A = _p(A_cat)       # not read by the backward (A_cat carries the factors); must be non-null
+        arr[i].dA, arr[i].dB, arr[i].dbias = _p(dA), _p(dB), _p(db)
+        arr[i].out_features, arr[i].r, arr[i].scale = fout, r, float(scale)
+        keep.append((W, B, dy))
+    dt_cat = torch.empty((T, R), dtype=torch.bfloat16, device=dev)
+    dx = torch.empty((T, fin), dtype=torch.bfloat16, device=dev) if need_dx else None
+    nws = lib.sow_group_workspace_bytes(_lib.OP_LINEAR_BWD, T, fin, arr, n)
     ws = workspace(dev, nws)
-    rc = lib.sow_linear_bwd_factors(_p(dy), _p(x), _p(t), _p(B), _p(dt), _p(dA), _p(dB), _p(dbias), T, fin, fout, r,
-                                    float(scale), SOWB_BF16, _p(ws), ws.numel(), _stream_ptr(dev))
-    check(rc, "sow_linear_bwd_factors")
-    launch_counter["kernels"] += 4 + (2 if want_dbias else 0)
-    return dt, dA, dB, dbias
+    rc = lib.sow_group_bwd(_p(x), _p(A_cat), _p(t_cat), arr, n, _p(dt_cat), _p(dx), T, fin, SOWB_BF16, _p(ws), ws.numel(),
+                           _stream_ptr(dev))
+    check(rc, "sow_group_bwd")
+    # K2 (one launch when the members share a cluster size, else n) + split-K dA + finalize + dX + colsum pairs
+    uniform = len({(m[1].shape[1], rank_pad(m[1].shape[0])) for m in members}) == 1
+    launch_counter["kernels"] += (1 if uniform else n) + 2 + (1 if need_dx else 0) + 2 * sum(1 for d in dbs if d is not None)
+    return dx, dAs, dBs, dbs
 
 
-def linear_bwd_dx(dy, dt, W, A):
-    _require_cuda(dy, dt, W, A)
-    lib = _lib.load()
-    T, fout = dy.shape
-    fin, r = A.shape
-    dx = torch.empty((T, fin), dtype=torch.bfloat16, device=dy.device)
-    nws = lib.sow_workspace_bytes(_lib.OP_LINEAR_BWD, T, fin, fout, r)
-    ws = workspace(dy.device, nws)
-    rc = lib.sow_linear_bwd_dx(_p(dy), _p(dt), _p(W), _p(A), _p(dx), T, fin, fout, r, SOWB_BF16, _p(ws), ws.numel(),
-                               _stream_ptr(dy.device))
-    check(rc, "sow_linear_bwd_dx")
-    launch_counter["kernels"] += 2
-    return dx
+def linear_fwd(x: torch.Tensor, W: Optional[torch.Tensor], A: torch.Tensor, B: torch.Tensor,
+               bias: Optional[torch.Tensor], scale: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Single projection = group of one.  Returns (y (T,out), A_pad (in,r_pad), t (T,r_pad))."""
+    _require_cuda(x, W, A, B, bias)
+    ys, A_cat, t_cat = group_fwd(x, [(W, A, B, bias, scale)])
+    return ys[0], A_cat, t_cat
+
+
+def linear_bwd(dy, x, A_pad, t, W, B, scale: float, want_dbias: bool, need_dx: bool = True):
+    """Returns (dx (T,in) or None, dA (in,r), dB (r,out), dbias or None)."""
+    dx, dAs, dBs, dbs = group_bwd(x, A_pad, t, [(W, B, dy, scale, True, True, want_dbias)], need_dx)
+    return dx, dAs[0], dBs[0], dbs[0]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -387,7 +439,7 @@ def adam_multi(chunks: torch.Tensor, dtype: torch.dtype, lr, beta1, beta2, eps, 
 # ---------------------------------------------------------------------------------------------------------
 # live profiling (bench.py)
 # ---------------------------------------------------------------------------------------------------------
-PROF_CLASSES = {"gemm_fwd": 0, "gemm_dx": 1, "gemm_skinny": 2, "gemm_splitk": 3, "merge": 4, "adam": 5}
+PROF_CLASSES = {"gemm_fwd": 0, "gemm_dx": 1, "gemm_skinny": 2, "gemm_splitk": 3, "merge": 4, "adam": 5, "gemm_k2": 6}
 
 
 def profile_enable(on: bool) -> None:

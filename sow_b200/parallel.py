@@ -40,8 +40,12 @@ class FlatGradSync:
     """Flat-bucket gradient averaging with backward overlap."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20,
-                 small_first: bool = True, overlap: bool = True):
+                 small_first: bool = True, overlap: bool = True, direct: Optional[Iterable[torch.nn.Parameter]] = None):
+        """``direct``: parameters whose backward kernels write the gradient straight into the bucket view (the SoW
+        factors: layer._grad_dst).  Their ``.grad`` is None between steps, the producing autograd node returns the
+        bucket view and AccumulateGrad adopts it -- no temporary gradient, no accumulate-add launch per factor."""
         params = [p for p in params if p.requires_grad]
+        self._direct = {id(p) for p in (direct or [])}
         # reverse registration order ~ order in which backward produces gradients
         order = list(reversed(params))
         self.buckets: List[dict] = []
@@ -64,22 +68,40 @@ class FlatGradSync:
         for bi, b in enumerate(self.buckets):
             for p in b["params"]:
                 self._p2b[id(p)] = bi
-                if overlap and hasattr(p, "register_post_accumulate_grad_hook"):
+                if hasattr(p, "register_post_accumulate_grad_hook") and (overlap or id(p) in self._direct):
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+        self._detach_direct()
 
     def _close(self, plist):
         total = sum(p.numel() for p in plist)
         flat = torch.zeros(total, dtype=plist[0].dtype, device=plist[0].device)
         off = 0
+        views = []
         for p in plist:
-            p.grad = flat[off:off + p.numel()].view_as(p)     # gradient becomes a view into the bucket
+            v = flat[off:off + p.numel()].view_as(p)
+            p.grad = v                                        # gradient becomes a view into the bucket
+            p._sow_grad_view = v
+            views.append(v)
             off += p.numel()
-        self.buckets.append({"params": plist, "flat": flat, "ready": 0, "work": None})
+        self.buckets.append({"params": plist, "flat": flat, "views": views, "ready": 0, "work": None})
+
+    def _detach_direct(self):
+        for b in self.buckets:
+            for p in b["params"]:
+                if id(p) in self._direct:
+                    p.grad = None
 
     # ---- backward overlap -------------------------------------------------------------------------------
     def _on_grad_ready(self, p):
         b = self.buckets[self._p2b[id(p)]]
+        v = p._sow_grad_view
+        if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+            # autograd bound its own tensor (it could not adopt the bucket view): move the gradient into the bucket
+            v.copy_(p.grad)
+            p.grad = v
         b["ready"] += 1
+        if not self.overlap:
+            return
         if b["ready"] == len(b["params"]) and self.world > 1 and b["work"] is None:
             b["work"] = self._launch(b["flat"])
 
@@ -107,11 +129,11 @@ class FlatGradSync:
     def zero_grad(self) -> None:
         for b in self.buckets:
             b["flat"].zero_()
-            off = 0
-            for p in b["params"]:
-                if p.grad is None or p.grad.data_ptr() != b["flat"].data_ptr() + off * b["flat"].element_size():
-                    p.grad = b["flat"][off:off + p.numel()].view_as(p)     # re-attach if someone set it to None
-                off += p.numel()
+            for p, v in zip(b["params"], b["views"]):
+                if id(p) in self._direct:
+                    p.grad = None                                          # the backward kernels write the view directly
+                elif p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    p.grad = v                                             # re-attach if someone set it to None
 
     def bytes_per_step(self) -> int:
         return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)

@@ -12,7 +12,7 @@ from typing import Iterable, List, Optional
 import torch
 import torch.nn as nn
 
-from .layer import SoWArgs, SoWLinear, accumulate_modules
+from .layer import SharedInputGroup, SoWArgs, SoWLinear, accumulate_modules
 
 try:  # peft is optional: only the base classes are used by the reference (prepare.py:13)
     from peft import PeftConfig as _PeftConfigBase, PeftModel as _PeftModelBase  # type: ignore
@@ -30,8 +30,9 @@ class SoWConfig(_PeftConfigBase):
     """Same fields as tn_gradient.prepare.SoWConfig (prepare.py:27-38)."""
 
     def __init__(self, target_modules, rank=16, scale=1.0, device="cpu", init_method="normal_QR", decompose="keep",
-                 **kwargs):
+                 fuse_shared_input=True, **kwargs):
         super().__init__(**kwargs)
+        self.fuse_shared_input = fuse_shared_input     # extension: group q/k/v and gate/up (group_shared_inputs)
         self.rank = rank
         self.scale = scale
         self.target_modules = target_modules
@@ -104,9 +105,35 @@ def prepare_sow(model: nn.Module, config=None, decompose=None, args: Optional[So
         else:
             setattr(model, name, layer)
         module.weight = None
+    if getattr(config, "fuse_shared_input", True):
+        group_shared_inputs(model)
     if torch.cuda.is_available():
         torch.cuda.empty_cache()
     return model
+
+
+# sibling projections that HF blocks call with the same hidden-state tensor (LlamaAttention / LlamaMLP,
+# RobertaSelfAttention): simple_train.py:318 and run_glue.py:572 list them as separate target modules
+SHARED_INPUT_SETS = (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"), ("query", "key", "value"))
+
+
+def group_shared_inputs(model: nn.Module, name_sets=SHARED_INPUT_SETS) -> int:
+    """Tie sibling SoW projections that read the same input into a SharedInputGroup: one pass over x
+    for all their rank-r down-projections and factor gradients, one dX launch.  Purely an execution plan: parameters,
+    state-dict keys and call sites are unchanged, and a group verifies at run time that its members really receive the
+    identical tensor (otherwise it switches itself off).  Returns the number of groups formed."""
+    formed = 0
+    for parent in model.modules():
+        kids = dict(parent.named_children())
+        for names in name_sets:
+            members = [kids[n] for n in names if isinstance(kids.get(n), SoWLinear)]
+            if len(members) < 2 or len({m.in_features for m in members}) != 1:
+                continue
+            grp = SharedInputGroup(members)
+            for m in members:
+                m._group = grp
+            formed += 1
+    return formed
 
 
 class SoWModel(_PeftModelBase):

@@ -124,7 +124,7 @@ class SoWTrainer:
         groups.append({"params": self.special, "lr": cfg.sow_lr, "weight_decay": cfg.weight_decay})
         self.optimizer = FusedAdamW(groups) if cfg.fused_optimizer else torch.optim.AdamW(groups)   # :502-506
         broadcast_parameters(model)                                                # DDP ctor semantics (:566-572)
-        self.grad_sync = FlatGradSync(self.trainable + self.special, overlap=cfg.overlap_grad_sync)
+        self.grad_sync = FlatGradSync(self.trainable + self.special, overlap=cfg.overlap_grad_sync, direct=self.special)
         self.global_step = 0
         self.update_step = 0
         self.merges = 0

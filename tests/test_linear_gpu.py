@@ -158,7 +158,7 @@ def test_unsupported_feature_size_fails_loudly():
     from sow_b200 import SowB200Error
     from tn_gradient.layer.sow import SoWLinear
     layer = SoWLinear(100, 5461 - 5461 % 2 + 1, bias=False, rank=4, init_method="normal", dtype=torch.bfloat16, device="cuda")
-    with pytest.raises(SowB200Error, match="multiples of 8"):
+    with pytest.raises(SowB200Error, match="multiple of 8"):
         layer(torch.randn(4, 100, device="cuda", dtype=torch.bfloat16))
 
 
@@ -227,7 +227,7 @@ def test_backward_as_first_cuda_work_of_the_autograd_thread():
         x = torch.randn(77, 328, device="cuda", dtype=torch.bfloat16, requires_grad=True)
         dy = torch.randn(77, 456, device="cuda", dtype=torch.bfloat16)
         y = layer(x)
-        y.backward(dy)                     # backward thread: first work is sow_linear_bwd_factors on new pointers
+        y.backward(dy)                     # backward thread: first work is sow_group_bwd on new pointers
         torch.cuda.synchronize()
         out["ok"] = bool(torch.isfinite(x.grad.float()).all())
 
@@ -235,3 +235,164 @@ def test_backward_as_first_cuda_work_of_the_autograd_thread():
     th.start()
     th.join()
     assert out.get("ok") is True
+
+
+# ---------------------------------------------------------------------------------------------------------
+# projections that share their input (q/k/v, gate/up): one autograd node per group
+# ---------------------------------------------------------------------------------------------------------
+
+class _Block(torch.nn.Module):
+    """q/k/v + gate/up call pattern of a transformer block: siblings are called with the identical tensor."""
+
+    def __init__(self, h, ff, bias=False):
+        super().__init__()
+        self.q_proj = torch.nn.Linear(h, h, bias=bias)
+        self.k_proj = torch.nn.Linear(h, h // 2, bias=bias)          # GQA-style narrower k/v
+        self.v_proj = torch.nn.Linear(h, h // 2, bias=bias)
+        self.gate_proj = torch.nn.Linear(h, ff, bias=bias)
+        self.up_proj = torch.nn.Linear(h, ff, bias=bias)
+        self.down_proj = torch.nn.Linear(ff, h, bias=bias)
+
+    def forward(self, x):
+        q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
+        a = q + torch.cat([k, v], dim=-1)
+        return self.down_proj(torch.nn.functional.silu(self.gate_proj(a)) * self.up_proj(a))
+
+
+def _mk_block(h, ff, r, fuse, decompose="keep", bias=False, seed=0):
+    from tn_gradient.prepare import SoWConfig, prepare_sow
+    torch.manual_seed(seed)
+    blk = _Block(h, ff, bias=bias)
+    cfg = SoWConfig(target_modules=["q_proj", "k_proj", "v_proj", "gate_proj", "up_proj", "down_proj"], rank=r,
+                    device="cuda", init_method="normal", decompose=decompose, fuse_shared_input=fuse)
+    blk = prepare_sow(blk, cfg).to("cuda", torch.bfloat16)
+    torch.manual_seed(seed + 1)
+    with torch.no_grad():
+        for m in blk.modules():
+            if hasattr(m, "upscale_weights"):
+                m.upscale_weights[0].normal_(0, 0.05)
+    return blk
+
+
+@pytest.mark.parametrize("decompose", ["keep", None])
+def test_shared_input_groups_match_ungrouped_execution(decompose):
+    """Grouped (one t_cat / dA_cat / dX launch per q/k/v and gate/up) vs one node per projection: same function, same
+    gradients up to the bf16 rounding of the differently-ordered fp32 sums."""
+    from sow_b200.layer import SharedInputGroup
+    h, ff, r = 512, 1376, 50
+    fused = _mk_block(h, ff, r, True, decompose)
+    plain = _mk_block(h, ff, r, False, decompose)
+    assert isinstance(fused.q_proj._group, SharedInputGroup) and fused.q_proj._group is fused.v_proj._group
+    assert fused.gate_proj._group is fused.up_proj._group and fused.down_proj._group is None
+    assert plain.q_proj._group is None
+    plain.load_state_dict(fused.state_dict())
+    x = torch.randn(4, 130, h, device="cuda", dtype=torch.bfloat16)
+    outs = []
+    for blk in (fused, plain):
+        xi = x.clone().requires_grad_(True)
+        y = blk(xi)
+        y.float().pow(2).mean().backward()
+        outs.append((y, xi.grad, {n: p.grad for n, p in blk.named_parameters() if p.grad is not None}))
+    torch.cuda.synchronize()
+    (y0, gx0, g0), (y1, gx1, g1) = outs
+    assert fused.q_proj._group.enabled and fused.q_proj._group.misses == 0 and fused.q_proj._group.cache is None
+    assert float((y0.float() - y1.float()).norm() / y1.float().norm()) < 5e-3
+    assert float((gx0.float() - gx1.float()).norm() / gx1.float().norm()) < 1e-2
+    assert set(g0) == set(g1) and len(g0) == 12
+    for k in g0:
+        assert float((g0[k].float() - g1[k].float()).norm() / (g1[k].float().norm() + 1e-20)) < 1e-2, k
+
+
+def test_shared_input_group_vs_oracle_with_bias_and_distinct_scales():
+    from tn_gradient.prepare import SoWConfig, prepare_sow
+
+    class Attn(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.query, self.key, self.value = (torch.nn.Linear(768, 768) for _ in range(3))
+
+        def forward(self, x):
+            return self.query(x), self.key(x), self.value(x)
+
+    torch.manual_seed(3)
+    att = prepare_sow(Attn(), SoWConfig(target_modules=["query", "key", "value"], rank=8, device="cuda",
+                                        init_method="normal", decompose="keep")).to("cuda", torch.bfloat16)
+    mods = [att.query, att.key, att.value]
+    for i, m in enumerate(mods):
+        m.scale = [0.125, 1.0, 0.5][i]
+        with torch.no_grad():
+            m.upscale_weights[0].normal_(0, 0.05)
+            m.bias.normal_(0, 0.1)
+    x = torch.randn(1000, 768, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    dys = [torch.randn(1000, 768, device="cuda", dtype=torch.bfloat16) for _ in range(3)]
+    ys = att(x)
+    torch.autograd.backward(ys, dys)
+    torch.cuda.synchronize()
+    xn = x.detach().float().cpu().numpy()
+    dx_o = 0
+    for m, y, dy in zip(mods, ys, dys):
+        W, A, B = (t.detach().float().cpu().numpy() for t in (m.acc_downweight, m.downscale_weights[0], m.upscale_weights[0]))
+        b = m.bias.detach().float().cpu().numpy()
+        dyn = dy.float().cpu().numpy()
+        y_o = O.sow_linear_forward(xn, W, [A], [B], b, m.scale, dtype=np.float32)
+        dxi, dA_o, dB_o, db_o = O.sow_linear_backward(dyn, xn, W, [A], [B], m.scale, dtype=np.float32)
+        dx_o = dx_o + dxi
+        assert rel_err(y.detach().float().cpu().numpy(), y_o) < TOL
+        assert rel_err(m.downscale_weights[0].grad.float().cpu().numpy(), dA_o[0]) < TOL
+        assert rel_err(m.upscale_weights[0].grad.float().cpu().numpy(), dB_o[0]) < TOL
+        assert rel_err(m.bias.grad.float().cpu().numpy(), db_o) < TOL
+    assert rel_err(x.grad.float().cpu().numpy(), dx_o) < TOL
+
+
+def test_group_switches_itself_off_when_inputs_differ():
+    from tn_gradient.prepare import SoWConfig, prepare_sow
+
+    class Odd(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_proj, self.up_proj = torch.nn.Linear(128, 256, bias=False), torch.nn.Linear(128, 256, bias=False)
+
+        def forward(self, x):
+            return self.gate_proj(x) + self.up_proj(x * 2.0)       # NOT the same tensor
+
+    torch.manual_seed(0)
+    m = prepare_sow(Odd(), SoWConfig(target_modules=["gate_proj", "up_proj"], rank=8, device="cuda", init_method="normal",
+                                     decompose="keep")).to("cuda", torch.bfloat16)
+    grp = m.gate_proj._group
+    x = torch.randn(64, 128, device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        ref = None
+        for _ in range(8):
+            y = m(x)
+            want = (x.float() @ m.gate_proj.acc_downweight.float() + (x.float() @ m.gate_proj.downscale_weights[0].float()) @ m.gate_proj.upscale_weights[0].float()
+                    + (2 * x.float()) @ m.up_proj.acc_downweight.float() + ((2 * x.float()) @ m.up_proj.downscale_weights[0].float()) @ m.up_proj.upscale_weights[0].float())
+            assert float((y.float() - want).norm() / want.norm()) < 1e-2
+    assert not grp.enabled and grp.cache is None
+
+
+def test_factor_gradients_land_in_the_flat_bucket_without_a_copy():
+    """FlatGradSync(direct=factors): the backward kernels write dA / dB straight into the bucket views and autograd adopts
+    them as .grad; values equal the ordinary path bit for bit; a second micro-step accumulates."""
+    from sow_b200.parallel import FlatGradSync
+    blk = _mk_block(256, 512, 8, True)
+    ref = _mk_block(256, 512, 8, True)
+    ref.load_state_dict(blk.state_dict())
+    factors = [p for n, p in blk.named_parameters() if "scale_weights" in n]
+    sync = FlatGradSync(factors, overlap=False, direct=factors)
+    assert all(p.grad is None for p in factors)
+    x = torch.randn(300, 256, device="cuda", dtype=torch.bfloat16)
+    blk(x).float().pow(2).mean().backward()
+    ref(x).float().pow(2).mean().backward()
+    flat = sync.buckets[0]["flat"]
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 2
+    for (n, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        if "scale_weights" in n:
+            assert lo <= p.grad.data_ptr() < hi and p.grad.data_ptr() == p._sow_grad_view.data_ptr(), n
+            assert torch.equal(p.grad, q.grad), n
+    blk(x).float().pow(2).mean().backward()                        # micro-step 2: accumulate onto the bucket
+    for (n, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        if "scale_weights" in n:
+            assert lo <= p.grad.data_ptr() < hi
+            assert float((p.grad.float() - 2 * q.grad.float()).norm() / (2 * q.grad.float().norm() + 1e-20)) < 1e-2, n
+    sync.zero_grad()
+    assert all(p.grad is None for p in factors) and float(flat.abs().max()) == 0.0
