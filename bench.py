@@ -28,7 +28,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="llama_350m")
+    ap.add_argument("--model", default="llama_350m",
+                    help="llama_{9m,60m,130m,350m,7b} (pre-training / keep fine-tune) or roberta_base (BASELINE.json configs[2]: "
+                         "GLUE-shaped fine-tune, mode keep, rank 8, seq 512, batch 16 -- pass those flags)")
     ap.add_argument("--rank", type=int, default=50)
     ap.add_argument("--batch", type=int, default=128,
                     help="sequences per GPU per step (128 = the reference's documented pre-training recipe, readme.md:5-26)")
@@ -37,6 +39,8 @@ def parse_args():
                     help="pretrain: empty accumulation, everything trains (config 2); keep: fine-tune of a dense model, "
                          "frozen base, only the factors train (configs 3-4)")
     ap.add_argument("--act-ckpt", action="store_true", help="activation checkpointing (config 4: Llama-7B)")
+    ap.add_argument("--param-dtype", default="bf16", choices=["bf16", "f32"],
+                    help="dtype of the model parameters (the reference's GLUE scripts never set one: fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-optimizer", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
@@ -209,7 +213,7 @@ def main():
     import torch
     import torch.distributed as dist
     from sow_b200 import ops
-    from sow_b200.trainer import LLAMA_SHAPES, SoWTrainer, TrainConfig
+    from sow_b200.trainer import SoWTrainer, TrainConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,16 +226,41 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     peaks = load_peaks()
 
-    cfg = TrainConfig(model=args.model, rank=args.rank, seq_len=args.seq, batch_size=args.batch,
-                      fused_optimizer=not args.no_fused_optimizer, decompose="keep" if args.mode == "keep" else None,
-                      freeze_base=args.mode == "keep", activation_checkpointing=args.act_ckpt,
-                      scale=1.0 if args.mode == "pretrain" else 0.125)
+    roberta = args.model.startswith("roberta")
+    if roberta:
+        args.mode = "keep"
+        # run_glue.py recipe (readme.md:30-67): lr 5e-5, sow_lr 1.2e-4, scale 1 until the first merge, then 1/rank
+        cfg = TrainConfig(model=args.model, rank=args.rank, seq_len=args.seq, batch_size=args.batch, lr=5e-5, sow_lr=1.2e-4,
+                          fused_optimizer=not args.no_fused_optimizer, decompose="keep", freeze_base=True,
+                          activation_checkpointing=args.act_ckpt, scale=1.0, scale_after_first_merge=1.0 / args.rank,
+                          dtype=torch.float32 if args.param_dtype == "f32" else torch.bfloat16)
+    else:
+        cfg = TrainConfig(model=args.model, rank=args.rank, seq_len=args.seq, batch_size=args.batch,
+                          fused_optimizer=not args.no_fused_optimizer, decompose="keep" if args.mode == "keep" else None,
+                          freeze_base=args.mode == "keep", activation_checkpointing=args.act_ckpt,
+                          scale=1.0 if args.mode == "pretrain" else 0.125,
+                          dtype=torch.float32 if args.param_dtype == "f32" else torch.bfloat16)
     trainer = SoWTrainer(cfg, device)
     B, S = args.batch, args.seq
     n_batches = 8
     gen = torch.Generator().manual_seed(1234 + rank)                      # per-rank stream
-    host_batches = [torch.randint(1, 32000, (B, S), generator=gen, dtype=torch.int64).pin_memory() for _ in range(n_batches)]
+    if roberta:
+        host_batches = [torch.randint(3, 50265, (B, S), generator=gen, dtype=torch.int64).pin_memory() for _ in range(n_batches)]
+        host_labels = [torch.randint(0, 2, (B,), generator=gen, dtype=torch.int64).pin_memory() for _ in range(n_batches)]
+    else:
+        host_batches = [torch.randint(1, 32000, (B, S), generator=gen, dtype=torch.int64).pin_memory() for _ in range(n_batches)]
+        host_labels = [None] * n_batches
     dev_batches = [b.to(device) for b in host_batches]
+    dev_labels = [None if l is None else l.to(device) for l in host_labels]
+    _step = trainer.step
+
+    class _T:          # trainer.step with the labels of the batch (sequence classification) or labels = input_ids (causal LM)
+        @staticmethod
+        def step(ids, i=None):
+            lab = None
+            if roberta:
+                lab = dev_labels[i % n_batches] if i is not None else dev_labels[0]
+            return _step(ids, labels=lab)
 
     def barrier():
         if world > 1:
@@ -241,7 +270,7 @@ def main():
     # ---- warm-up: W steps, the first followed by a merge so that the timed steps see a dense W --------------
     W = max(args.warmup, 3)
     for i in range(W):
-        loss = trainer.step(dev_batches[i % n_batches])
+        loss = _T.step(dev_batches[i % n_batches], i)
         if i == 0:
             trainer.merge()
     barrier()
@@ -256,7 +285,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        loss = trainer.step(dev_batches[i % n_batches])
+        loss = _T.step(dev_batches[i % n_batches], i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -275,7 +304,8 @@ def main():
     e0.record()
     for i in range(K):
         ids = host_batches[i % n_batches].to(device, non_blocking=True)   # H2D of this step's inputs (pinned)
-        loss = trainer.step(ids)
+        lab = host_labels[i % n_batches].to(device, non_blocking=True) if roberta else None
+        loss = trainer.step(ids, labels=lab)
         _ = loss.item()                                                    # D2H of the step's result
     e1.record()
     barrier()
@@ -287,7 +317,7 @@ def main():
     # ---- instrumented pass: CUDA events around every kernel of each class (not part of `value`) -------------
     ops.profile_enable(True)
     for i in range(args.profile_steps):
-        trainer.step(dev_batches[i % n_batches])
+        _T.step(dev_batches[i % n_batches], i)
     torch.cuda.synchronize()
     kern = {}
     for k in ops.PROF_CLASSES:
@@ -303,7 +333,7 @@ def main():
     for i in range(5):
         torch.cuda.synchronize()
         ops.profile_enable(True)
-        trainer.step(dev_batches[i % n_batches])
+        _T.step(dev_batches[i % n_batches], i)
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tw = time.perf_counter()
         m0.record()
@@ -404,45 +434,77 @@ def main():
     extra_kernels["gemm_fwd_ms_per_step"] = kern["gemm_fwd"]["ms_total"] / args.profile_steps
     extra_kernels["gemm_dx_ms_per_step"] = kern["gemm_dx"]["ms_total"] / args.profile_steps
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle port of the reference's CPU path on the host cores ----
+    # ---- multi-GPU correctness (world > 1): replicas must hold identical parameters after the timed steps, and identical
+    # merged W / re-initialised A after one more merge (raises on a mismatch)
+    replicas = None
+    if world > 1:
+        from sow_b200.parallel import assert_replicas_consistent
+        from sow_b200.surgery import sow_modules
+        assert_replicas_consistent(list(trainer.model.parameters()), "parameter after the timed steps")
+        _T.step(dev_batches[0], 0)
+        trainer.merge()
+        mods = sow_modules(trainer.model)
+        assert_replicas_consistent([m.acc_downweight for m in mods], "merged W")
+        assert_replicas_consistent([a for m in mods for a in m.downscale_weights], "re-initialised A")
+        replicas = {"consistent": True, "checked": "all parameters after the timed steps; merged W and re-initialised A of "
+                    f"{len(mods)} SoW layers after one more merge (bit-exact across {world} ranks)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's CPU path on the host cores -- the UNMODIFIED reference from
+    # baseline/_ref when it is there (kind "reference"), else the oracle port ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_trainer import time_cpu_training
-        res = time_cpu_training(args.model, args.rank, batch=2, seq_len=S, steps=3, warmup=1)
-        cpu_baseline = {"value": res["tokens_per_s"], "unit": "tokens/s", "cores": res["threads"], "kind": "port",
-                        "sample": f"3 steps of 2x{S} tokens ({args.model} SoW r={args.rank}, fp32, merge in warm-up), "
-                                  f"{res['sec_per_step']:.2f} s/step"}
+        res = run_ref_subprocess(ref_workload_args(args) + ["--batch", 2, "--steps", 3, "--warmup", 1, "--device", "cpu",
+                                                            "--dtype", "f32", "--merge-at", 0])
+        kind = "reference"
+        if res is None and not roberta:
+            from oracle.cpu_trainer import time_cpu_training
+            res = time_cpu_training(args.model, args.rank, batch=2, seq_len=S, steps=3, warmup=1)
+            kind = "port"
+        if res is not None:
+            cpu_baseline = {"value": res["tokens_per_s"], "unit": "tokens/s", "cores": res["threads"], "kind": kind,
+                            "sample": f"3 steps of 2x{S} tokens ({args.model} SoW r={args.rank}, fp32, merge in warm-up), "
+                                      f"{res['sec_per_step']:.2f} s/step"}
 
-    # ---- the reference's own eager formulation on the SAME GPU (oracle port in bf16 on cuda; rank 0, N=1 only):
-    # the practical bar of BASELINE.md section 5, reported beside the CPU baseline, not part of `value`
+    # ---- the reference itself on the SAME GPU at the SAME config (rank 0, N=1 only): stock tn_gradient.SoWLinear /
+    # prepare_sow / accumulate from baseline/_ref, eager cuBLAS + torch.optim.AdamW, in its own process -- the practical
+    # bar of BASELINE.md section 5, reported beside the CPU baseline, not part of `value`
     gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del trainer
         torch.cuda.empty_cache()
-        from oracle.cpu_trainer import time_cpu_training
-        res = time_cpu_training(args.model, args.rank, batch=B, seq_len=S, steps=5, warmup=3, device=str(device),
-                                dtype=torch.bfloat16)
-        gpu_eager = {"value": res["tokens_per_s"], "unit": "tokens/s", "kind": "port (eager torch ops of the reference, bf16, "
-                     "torch.optim.AdamW) on the same B200", "sample": f"5 steps of {B}x{S} tokens, {res['sec_per_step'] * 1e3:.1f} ms/step",
-                     "speedup_of_this_build": value / res["tokens_per_s"]}
+        pd = "f32" if args.param_dtype == "f32" else "bf16"
+        res = run_ref_subprocess(ref_workload_args(args) + ["--batch", B, "--steps", 5, "--warmup", 3, "--device", "cuda",
+                                                            "--dtype", pd, "--merge-at", 0])
+        kind = f"reference (unmodified package from baseline/_ref, eager torch ops, {pd}, torch.optim.AdamW) on the same B200"
+        if res is None and not roberta:
+            from oracle.cpu_trainer import time_cpu_training
+            res = time_cpu_training(args.model, args.rank, batch=B, seq_len=S, steps=5, warmup=3, device=str(device),
+                                    dtype=torch.bfloat16)
+            kind = "port (eager torch ops of the reference, bf16, torch.optim.AdamW) on the same B200"
+        if res is not None:
+            gpu_eager = {"value": res["tokens_per_s"], "unit": "tokens/s", "kind": kind, "same_config": True,
+                         "sample": f"5 steps of {B}x{S} tokens, {res['sec_per_step'] * 1e3:.1f} ms/step",
+                         "speedup_of_this_build": value / res["tokens_per_s"]}
 
     if rank == 0:
         line = {
             "metric": "train_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16" if args.param_dtype == "bf16" else "f32 parameters, bf16x3 tensor-core products", "data": "synthetic",
             "config": {
                 "workload": workload_name(args),
                 "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "tokens_per_step": tokens_per_step,
                 "parallelism": f"dp{world}", "l2": "working set per step (>1 GB weights+activations) exceeds the 126 MB L2; no flush needed",
                 "optimizer": "FusedAdamW (sow_adam_multi)" if cfg.fused_optimizer else "torch.optim.AdamW",
             },
-            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8 + (B * 8 if roberta else 0),
+                    "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "roofline": roofline,
             "kernels": extra_kernels,
             "cpu_baseline": cpu_baseline,
             "gpu_eager_baseline": gpu_eager,
+            "replicas": replicas,
             "clocks": clocks,
             "loss": final_loss,
         }

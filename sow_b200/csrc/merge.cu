@@ -47,6 +47,10 @@ constexpr int kMgABytes = kMgBM * 64 * 2;           // 16 KB (operand tile and s
 constexpr int kMgSlotBytes = kMgWBytes;
 constexpr int kMgStrip = 4;                         // column tiles per strip (B tiles resident in smem)
 constexpr int kMgAcc = 4;                           // TMEM accumulator stages
+// W tiles pulled into L2 (cp.async.bulk.prefetch.tensor) ahead of the slot that will load them.  OFF: measured on B200
+// (Llama-350M r=50, 20 merges each) distance 0 / 4 / 6 / 10 / 16 -> 0.250 / 0.351 / 0.366 / 0.377 / 0.379 ms: the
+// prefetches compete with the demand loads for the same TMA unit and L2 slots.  SOWB_MERGE_PREFETCH=<n> re-enables it.
+constexpr int kMgPrefetchDefault = 0;
 constexpr int kMgMaxEntries = 384;                  // per launch (longer tables are split by the host)
 constexpr int kMgNumBars = 3 * kMgSlots + 2 * kMgAcc + 3 + 2 * kMgStrip;   // + one 8-byte cell for the TMEM address
 constexpr int kMgBarBytes = 320;
@@ -154,7 +158,8 @@ struct MergeCursor {
 };
 
 __global__ void __launch_bounds__(kMgThreads, 1)
-sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total_tiles, long long* __restrict__ dbg_ts) {
+sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total_tiles, int prefetch,
+                 long long* __restrict__ dbg_ts) {
   // debug timeline (SOWB_MERGE_TS): CTA 0 records clock64 stamps per tile: [tile][8]
   auto stamp = [&](int tile_local, int k) {
     if (dbg_ts != nullptr && blockIdx.x == 0 && tile_local < 256) dbg_ts[tile_local * 8 + k] = clock64();
@@ -230,12 +235,24 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
   if (warp == 8) {
     if (lane == 0 && lo < hi) {
       // ===================== TMA producer =====================
-      MergeCursor c;
+      MergeCursor c, pf;                  // pf runs kMgPrefetch tiles ahead and pulls W tiles from HBM into L2
       c.init(tab, info, n_entries, lo);
+      pf.init(tab, info, n_entries, lo);
+      int pf_tile = lo;
       int slot = 0;
       uint32_t phase = 0, b_phases = 0;   // b_phases: one parity bit per resident B tile
       const uint64_t pol_keep = l2_policy_evict_last();
       for (int tile = lo; tile < hi; ++tile) {
+        // optional (off by default, see kMgPrefetchDefault): deepen the HBM pipeline beyond the 3 shared-memory slots
+        while (prefetch > 0 && pf_tile < hi && pf_tile <= tile + prefetch) {
+          pf.seek(pf_tile, lo, hi - 1);
+          if (pf_tile > tile + kMgSlots - 1 && pf.e->has_prev) {
+            if (pf.entry_changed) tma_acquire_desc(&pf.g->tmWin);
+            tma_prefetch_l2_2d(&pf.g->tmWin, pf.n0, pf.m0);
+            tma_prefetch_l2_2d(&pf.g->tmWin, pf.n0 + 64, pf.m0);
+          }
+          ++pf_tile;
+        }
         c.seek(tile, lo, hi - 1);
         const MergeInfo* e = c.e;
         if (c.entry_changed) {
@@ -612,8 +629,12 @@ int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* t
                                       cudaMemcpyHostToDevice, stream));
       const int grid = tiles < sms ? tiles : sms;
       ProfileScope prof(stream, PROF_MERGE, bytes);
+      static const int prefetch = []() {
+        const char* e = getenv("SOWB_MERGE_PREFETCH");   // tuning knob: tiles of L2 prefetch distance (0 = off)
+        return e ? atoi(e) : kMgPrefetchDefault;
+      }();
       sow_merge_kernel<<<grid, kMgThreads, kMgSmemTotal, stream>>>(static_cast<const MergeDevEntry*>(table_dev),
-                                                                   static_cast<int>(cnt), tiles, g_merge_ts);
+                                                                   static_cast<int>(cnt), tiles, prefetch, g_merge_ts);
       SOWB_CHECK_CUDA(cudaGetLastError());
     }
   }

@@ -95,6 +95,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// Pull a tile from HBM into L2 ahead of the TMA load that will consume it (no shared-memory slot needed).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // L2 eviction-priority policies for streaming (evict_first) and re-used (evict_last) data
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;

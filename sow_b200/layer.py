@@ -419,10 +419,14 @@ def _merge_factored(mod: SoWLinear) -> None:
 
 
 def _reinit(mods: List[SoWLinear], sync: bool) -> None:
-    """A <- QR-init / N(0, .02), B <- 0 (sow.py:157-178); .data swap keeps Parameter identity.
+    """A <- QR-init / N(0, .02), B <- 0 (sow.py:157-178).  The new values are copied INTO the existing factor storage
+    (one multi-tensor copy, one multi-tensor zero fill): Parameter identity is preserved as with the reference's
+    ``.data`` swap, every factor keeps its own storage, and the addresses the fused optimizer / gradient buckets / CUDA
+    graphs hold stay valid.
 
-    With torch.distributed initialised and ``sync`` the new A is broadcast from rank 0, which makes the replicas
-    consistent by construction (the reference relies on identical RNG state on every rank)."""
+    With torch.distributed initialised and ``sync`` the new A is broadcast from rank 0 -- ONE broadcast per batch of
+    same-shaped factors -- which makes the replicas consistent by construction (the reference relies on identical RNG
+    state on every rank)."""
     import torch.distributed as dist
     do_sync = sync and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     # batch the thin QRs of all normal_QR modules that share (in, rank, device)
@@ -431,7 +435,7 @@ def _reinit(mods: List[SoWLinear], sync: bool) -> None:
         if mod.init_method == "normal_QR":
             dev = mod.downscale_weights[0].device
             groups.setdefault((mod.in_features, mod.rank, dev), []).append(mod)
-    new_A = {}
+    dst, src, zeros = [], [], []
     for (fin, r, dev), ms in groups.items():
         n = sum(m.n_iter for m in ms)
         # the reference draws in the accumulation dtype (bf16-rounded Gaussian, sow.py:163-165,170)
@@ -440,24 +444,29 @@ def _reinit(mods: List[SoWLinear], sync: bool) -> None:
         if wdt != torch.float32:
             G = G.to(wdt).to(torch.float32)
         Q = ops.thin_qr(G, r)
+        if do_sync:
+            dist.broadcast(Q, src=0)
         k = 0
         for m in ms:
             for i in range(m.n_iter):
-                new_A[(id(m), i)] = Q[k]
+                dst.append(m.downscale_weights[i].data)
+                src.append(Q[k])
                 k += 1
     for mod in mods:
-        downs, ups = [], []
-        for i, (a, b) in enumerate(zip(mod.downscale_weights, mod.upscale_weights)):
-            if mod.init_method == "normal_QR":
-                a_new = new_A[(id(mod), i)].to(a.dtype)
-            else:
-                a_new = torch.empty_like(a).normal_(std=0.02)
-            if do_sync:
-                dist.broadcast(a_new, src=0)
-            downs.append(a_new.contiguous())
-            ups.append(torch.zeros_like(b))
-        mod.downscale_weights.from_weights(downs)
-        mod.upscale_weights.from_weights(ups)
+        if mod.init_method != "normal_QR":
+            for a in mod.downscale_weights:
+                a.data.normal_(std=0.02)
+                if do_sync:
+                    dist.broadcast(a.data, src=0)
+        zeros += [b.data for b in mod.upscale_weights]
+    if dst:
+        try:
+            torch._foreach_copy_(dst, src)
+        except Exception:                                  # older torch: no mixed-dtype foreach copy
+            for d, s_ in zip(dst, src):
+                d.copy_(s_)
+    if zeros:
+        torch._foreach_zero_(zeros)
 
 
 @torch.no_grad()

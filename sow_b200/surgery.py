@@ -178,7 +178,11 @@ def load_sow(model: nn.Module, checkpoint_path: str) -> None:
             else:
                 setattr(model, name, new)
         else:
-            obj.data.copy_(value.data)
+            with torch.no_grad():
+                obj.copy_(value.to(obj.device))        # in-place through the Parameter: bumps its version counter
+    for m in sow_modules(model):                       # compute copies of W derived from the old values are stale now
+        m._w_shadow = None
+        m._w_shadow_key = None
 
 
 def _device_of(model: nn.Module) -> torch.device:

@@ -28,6 +28,12 @@ LLAMA_SHAPES: Dict[str, Dict[str, int]] = {
     "llama_7b": dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32),
 }
 LLAMA_TARGETS = ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]   # simple_train.py:318
+ROBERTA_TARGETS = ["query", "key", "value", "output.dense", "intermediate.dense"]               # run_glue.py:572
+# scripts/configs/roberta.json (RoBERTa-base): data, not code
+ROBERTA_SHAPES: Dict[str, Dict[str, int]] = {
+    "roberta_base": dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12),
+    "roberta_tiny": dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4),
+}
 
 
 def build_llama(name: str, seq_len: int = 256, vocab_size: int = 32000, seed: int = 42,
@@ -48,6 +54,18 @@ def build_llama(name: str, seq_len: int = 256, vocab_size: int = 32000, seed: in
         return LlamaForCausalLM(cfg)
     finally:
         torch.set_default_dtype(prev)
+
+
+def build_roberta(name: str = "roberta_base", seq_len: int = 512, num_labels: int = 2, seed: int = 42,
+                  dropout: float = 0.1) -> nn.Module:
+    """Random-init HF RoBERTa sequence classifier of the reference's GLUE config (run_glue.py:508-516 loads
+    AutoModelForSequenceClassification; no checkpoint is reachable offline, so the weights are random-init)."""
+    from transformers import RobertaConfig, RobertaForSequenceClassification
+    cfg = RobertaConfig(vocab_size=50265, hidden_act="gelu", hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout,
+                        max_position_embeddings=max(514, seq_len + 2), type_vocab_size=1, layer_norm_eps=1e-5, pad_token_id=1,
+                        bos_token_id=0, eos_token_id=2, num_labels=num_labels, **ROBERTA_SHAPES[name])
+    torch.manual_seed(seed)
+    return RobertaForSequenceClassification(cfg)
 
 
 def reset_optimizer(optimizer: torch.optim.Optimizer, group_id: int) -> None:
@@ -87,19 +105,36 @@ class TrainConfig:
     overlap_grad_sync: bool = True
     decompose: Optional[str] = None      # None: pre-training (empty accumulation); "keep": fine-tuning of a dense model
     freeze_base: bool = False            # fine-tuning: only the SoW factors train (run_glue.py:515-516,547-553)
+    scale_after_first_merge: Optional[float] = None   # run_glue.py:996-1001 sets module.scale = 1/rank after the first merge
+    dropout: float = 0.1                 # RoBERTa only (scripts/configs/roberta.json)
 
 
 class SoWTrainer:
     """One process per GPU.  ``step(input_ids)`` = one micro-step of simple_train.py's loop body."""
 
-    def __init__(self, cfg: TrainConfig, device: torch.device):
+    def __init__(self, cfg: TrainConfig, device: torch.device, model: Optional[nn.Module] = None,
+                 targets: Optional[list] = None):
+        """``model``: an already built (and possibly already SoW-prepared) module to train instead of the named config;
+        ``targets``: its SoW target module names."""
         self.cfg = cfg
         self.device = device
-        big = LLAMA_SHAPES[cfg.model]["hidden_size"] >= 2048
-        model = build_llama(cfg.model, cfg.seq_len, seed=cfg.seed, dtype=cfg.dtype if big else None)
-        sow_cfg = SoWConfig(target_modules=LLAMA_TARGETS, rank=cfg.rank, init_method=cfg.init_method, scale=cfg.scale,
-                            decompose=cfg.decompose, device=str(device))
-        model = prepare_sow(model, sow_cfg)                                        # simple_train.py:318-331
+        self.is_classifier = cfg.model.startswith("roberta")
+        if model is None:
+            if self.is_classifier:
+                model = build_roberta(cfg.model, cfg.seq_len, seed=cfg.seed, dropout=cfg.dropout)
+                targets = targets or ROBERTA_TARGETS
+            else:
+                big = LLAMA_SHAPES[cfg.model]["hidden_size"] >= 2048
+                model = build_llama(cfg.model, cfg.seq_len, seed=cfg.seed, dtype=cfg.dtype if big else None)
+                targets = targets or LLAMA_TARGETS
+        from .layer import SoWLinear
+        if not any(isinstance(m, SoWLinear) for m in model.modules()):
+            if cfg.freeze_base and self.is_classifier:
+                for p in model.roberta.parameters():                               # run_glue.py:515-516
+                    p.requires_grad = False
+            sow_cfg = SoWConfig(target_modules=targets or LLAMA_TARGETS, rank=cfg.rank, init_method=cfg.init_method,
+                                scale=cfg.scale, decompose=cfg.decompose, device=str(device))
+            model = prepare_sow(model, sow_cfg)                                    # simple_train.py:318-331
         special, ids = [], set()
         for m in sow_modules(model):                                                # simple_train.py:389-405
             for p in list(m.downscale_weights) + list(m.upscale_weights):
@@ -110,10 +145,12 @@ class SoWTrainer:
             if cfg.freeze_base and hasattr(model, "enable_input_require_grads"):
                 model.enable_input_require_grads()       # frozen embeddings: keep the checkpointed segments differentiable
         model = model.to(device=device, dtype=cfg.dtype)                           # simple_train.py:425-428
-        if cfg.freeze_base:
+        if cfg.freeze_base and not self.is_classifier:
             for p in model.parameters():
                 if id(p) not in ids:
                     p.requires_grad_(False)
+        for p in special:
+            p.requires_grad_(True)
         self.trainable = [p for p in model.parameters() if p.requires_grad and id(p) not in ids]
         self.special = special
         self.model = model
@@ -129,12 +166,14 @@ class SoWTrainer:
         self.update_step = 0
         self.merges = 0
 
-    def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None,
+             attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         cfg = self.cfg
         self.global_step += 1
         if labels is None:
             labels = input_ids
-        loss = self.model(input_ids=input_ids, labels=labels).loss                 # simple_train.py:611
+        kw = {} if attention_mask is None else {"attention_mask": attention_mask}
+        loss = self.model(input_ids=input_ids, labels=labels, **kw).loss           # simple_train.py:611 / run_glue.py:978
         (loss / cfg.gradient_accumulation).backward()                              # :612-613 (+ overlapped all-reduce)
         accumulation_step = int(cfg.gradient_accumulation * cfg.sow_accumulation)
         G = cfg.gradient_accumulation
@@ -155,6 +194,9 @@ class SoWTrainer:
         accumulate(self.model)
         reset_optimizer(self.optimizer, group_id=self.sow_group_id)
         self.merges += 1
+        if self.merges == 1 and self.cfg.scale_after_first_merge is not None:      # run_glue.py:996-1001
+            for m in sow_modules(self.model):
+                m.scale = self.cfg.scale_after_first_merge
 
     def tokens_per_step(self) -> int:
         return self.cfg.batch_size * self.cfg.seq_len
