@@ -65,11 +65,13 @@ int sow_rank_pad(int r);
  */
 typedef struct sowb_group_member {
   const void* W;    /* (in,out) frozen accumulation acc_downweight, or NULL before the first merge (sow.py:69-70) */
+  const void* W_lo; /* SOWB_F32 mode: low bf16 piece of W (W ~ W + W_lo), else NULL                               */
   const void* A;    /* (in,r)   downscale_weights[i]                                                              */
   const void* B;    /* (r,out)  upscale_weights[i]                                                                */
   const void* bias; /* (out) or NULL                                              [forward]                      */
   void* y;          /* (T,out) output                                             [forward]                      */
   const void* dy;   /* (T,out) upstream gradient                                  [backward]                     */
+  const void* dy_lo;/* SOWB_F32 mode: low bf16 piece of dY, else NULL             [backward]                     */
   void* dA;         /* (in,r)  gradient of A, or NULL                             [backward]                     */
   void* dB;         /* (r,out) gradient of B, or NULL                             [backward]                     */
   void* dbias;      /* (out)   gradient of bias, or NULL                          [backward]                     */
@@ -88,9 +90,19 @@ size_t sow_group_workspace_bytes(int op, int64_t T, int in, const sowb_group_mem
  * (x is read once instead of n times), and each y_i is one tcgen05 GEMM with the t_i . B_i product fused in as an extra
  * K-segment.  A_cat and t_cat (caller-allocated bf16) are what autograd saves for sow_group_bwd.
  * W_i may be NULL (pre-merge phase) -> rank-r term only.  1 <= n <= 4.
+ *
+ * dtype SOWB_BF16: everything bf16.  dtype SOWB_F32 (fp32 modules -- the reference's GLUE scripts never set a dtype,
+ * run_glue.py:386-388,508-514): the fp32 operands arrive split into two bf16 pieces each (sow_split_bf16x2: v ~ hi + lo,
+ * relative error 2^-17), x = (x, x_lo), W_i = (W, W_lo), and the base product runs as the bf16x3 contraction
+ * x.W + x.W_lo + x_lo.W on the tensor cores with fp32 accumulation (fp32-faithful: ~1e-5 relative, vs 4e-3 for plain bf16
+ * and 5e-4 for TF32); y_i and bias_i are fp32.  The rank-r factors A_i, B_i are passed rounded to bf16 (their products
+ * are two orders of magnitude smaller than the base term).
  */
-int sow_group_fwd(const void* x, const sowb_group_member* members_host, int n, void* A_cat, void* t_cat, int64_t T,
-                  int in, int dtype, void* stream);
+int sow_group_fwd(const void* x, const void* x_lo, const sowb_group_member* members_host, int n, void* A_cat, void* t_cat,
+                  int64_t T, int in, int dtype, void* stream);
+
+/* v (fp32, n elements) -> hi = bf16(v), lo = bf16(v - hi): the two pieces the SOWB_F32 mode consumes. */
+int sow_split_bf16x2(const float* src, void* hi, void* lo, int64_t n, void* stream);
 
 /*
  * Backward of a group.   Replaces the MmBackward nodes autograd records at sow.py:112,117,119 for every member:
@@ -100,7 +112,9 @@ int sow_group_fwd(const void* x, const sowb_group_member* members_host, int n, v
  *     dbias_i = sum_T dY_i                 (if non-NULL)
  * The full in x out weight gradient is never formed (W is frozen: sow.py:69-70, prepare.py:142,150).  All reductions
  * across CTAs go through fp32 partials summed in a fixed order: results are bit-reproducible run to run.
- * dt_cat[T,R] bf16 is caller-allocated scratch.  At most 3 members may carry a dense W.
+ * dt_cat[T,R] bf16 is caller-allocated scratch.  At most 4 (SOWB_F32: 3) members may carry a dense W.
+ * SOWB_F32: dY_i = (dy, dy_lo) and W_i = (W, W_lo) are bf16 pieces, dX is fp32 (bf16x3 products); the factor gradients
+ * are computed from the high pieces and written in bf16.
  */
 int sow_group_bwd(const void* x, const void* A_cat, const void* t_cat, const sowb_group_member* members_host, int n,
                   void* dt_cat, void* dx, int64_t T, int in, int dtype, void* ws, size_t ws_bytes, void* stream);
@@ -119,7 +133,9 @@ typedef struct sowb_merge_entry {
   float scale;
 } sowb_merge_entry;
 
-/* Grouped merge over n entries in ONE launch.  table_dev: device scratch of n * sow_merge_table_stride() bytes. */
+/* Grouped merge over n entries in ONE launch.  table_dev: device scratch of n * sow_merge_table_stride() bytes.
+ * dtype SOWB_BF16: W, A, B bf16, the rank-r product on tcgen05, fp32 accumulate, one bf16 rounding of W.
+ * dtype SOWB_F32 : W, A, B fp32, exact fp32 FMA (fp32 modules keep their pretrained weights at full precision). */
 size_t sow_merge_table_stride(void);
 int sow_merge_grouped(const sowb_merge_entry* entries_host, int n, int dtype, void* table_dev,
                       size_t table_bytes, void* stream);

@@ -43,11 +43,13 @@ class GroupMember(ctypes.Structure):
     """sowb_group_member (include/sow_b200.h)."""
     _fields_ = [
         ("W", ctypes.c_void_p),
+        ("W_lo", ctypes.c_void_p),
         ("A", ctypes.c_void_p),
         ("B", ctypes.c_void_p),
         ("bias", ctypes.c_void_p),
         ("y", ctypes.c_void_p),
         ("dy", ctypes.c_void_p),
+        ("dy_lo", ctypes.c_void_p),
         ("dA", ctypes.c_void_p),
         ("dB", ctypes.c_void_p),
         ("dbias", ctypes.c_void_p),
@@ -68,7 +70,8 @@ SIGNATURES = {
     "sow_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "sow_rank_pad": (_i, [_i]),
     "sow_group_workspace_bytes": (_sz, [_i, _i64, _i, ctypes.POINTER(GroupMember), _i]),
-    "sow_group_fwd": (_i, [_vp, ctypes.POINTER(GroupMember), _i, _vp, _vp, _i64, _i, _i, _vp]),
+    "sow_group_fwd": (_i, [_vp, _vp, ctypes.POINTER(GroupMember), _i, _vp, _vp, _i64, _i, _i, _vp]),
+    "sow_split_bf16x2": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "sow_group_bwd": (_i, [_vp, _vp, _vp, ctypes.POINTER(GroupMember), _i, _vp, _vp, _i64, _i, _i, _vp, _sz, _vp]),
     "sow_merge_table_stride": (_sz, []),
     "sow_merge_grouped": (_i, [ctypes.POINTER(MergeEntry), _i, _i, _vp, _sz, _vp]),

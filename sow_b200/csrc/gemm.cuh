@@ -38,9 +38,10 @@ enum EpiMode : int {
   EPI_BF16_TMA = 0,    // D -> bf16, via smem staging + TMA store (clips M/N tails)
   EPI_F32_PARTIAL = 1,  // D -> fp32 PARTIAL of split s stored at out_f32[s*split_stride + row*ldc + col]; the caller sums the
                        // splits in a fixed order (bit-reproducible, unlike red.global.add; no zero-fill needed)
+  EPI_F32_TMA = 2,     // D -> fp32 (+ fp32 bias), via smem staging + TMA store: the output of the bf16x3 path of fp32 modules
 };
 
-constexpr int kMaxSeg = 4;
+constexpr int kMaxSeg = 10;   // 3 members x 3 bf16x3 pieces + the rank-r tail
 constexpr int kMaxAlphaBlocks = 16;   // per-64-column alpha table covers N <= 1024 (wider outputs use alpha[0])
 
 struct GemmMaps {
@@ -58,6 +59,7 @@ struct GemmParams {
   int alpha_blocks;     // 0: alpha[0] for every column; else alpha[(col / 64)]
   float alpha[kMaxAlphaBlocks];
   const __nv_bfloat16* bias;  // nullable, length N (EPI_BF16_TMA only)
+  const float* bias_f32;      // nullable, length N (EPI_F32_TMA only)
   float* out_f32;             // EPI_F32_PARTIAL only
   int64_t split_stride;       // EPI_F32_PARTIAL only: elements between the partial outputs of consecutive splits
   int ldc;
@@ -101,7 +103,7 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       tma_prefetch_desc(&maps.a[sg]);
       tma_prefetch_desc(&maps.b[sg]);
     }
-    if (EPI == EPI_BF16_TMA) tma_prefetch_desc(&maps.c);
+    if (EPI != EPI_F32_PARTIAL) tma_prefetch_desc(&maps.c);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S::kStages; ++i) {
@@ -271,6 +273,42 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
           ++boxes_issued;
         }
+      } else if (EPI == EPI_F32_TMA) {
+        // one 32-column fp32 box (128 B per row) per TMEM load; same double-buffered staging as the bf16 path
+#pragma unroll 1
+        for (int b = 0; b < BN / 32; ++b) {
+          if (n0 + b * 32 >= p.N) break;  // uniform across the CTA
+          uint8_t* stg = staging + (boxes_issued & 1) * kStageCBytes;
+          if (boxes_issued >= 2) {
+            if (et == 0) tma_store_wait_read<1>();
+            named_barrier_sync(1, kEpiThreads);
+          }
+          const float alpha = p.alpha[p.alpha_blocks ? min(p.alpha_blocks - 1, (n0 + b * 32) >> 6) : 0];
+          uint32_t v[32];
+          tmem_ld32(taddr + b * 32, v);
+          tmem_ld_wait();
+          const int colbase = n0 + b * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float f[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[j] = alpha * __uint_as_float(v[c * 4 + j]);
+              if (p.bias_f32 != nullptr) {
+                const int col = colbase + c * 4 + j;
+                if (col < p.N) f[j] += p.bias_f32[col];
+              }
+            }
+            *reinterpret_cast<float4*>(stg + row_in_tile * 128 + ((c ^ (row_in_tile & 7)) << 4)) = make_float4(f[0], f[1], f[2], f[3]);
+          }
+          fence_proxy_async_smem();
+          named_barrier_sync(1, kEpiThreads);
+          if (et == 0) {
+            tma_store_2d(&maps.c, stg, n0 + b * 32, m0);
+            tma_store_commit();
+          }
+          ++boxes_issued;
+        }
       } else {
         const int row = m0 + row_in_tile;
         const int split = w % p.splits;
@@ -306,7 +344,7 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         acc_phase ^= 1;
       }
     }
-    if (EPI == EPI_BF16_TMA && et == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores
+    if (EPI != EPI_F32_PARTIAL && et == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores
   }
 
   tc_fence_before();

@@ -80,6 +80,35 @@ __global__ void finalize_jobs_kernel(const FinJobs jobs) {
     J.dst[static_cast<int64_t>(ocol) * J.ld_dst + orow] = __float2bfloat16(tile[threadIdx.x][threadIdx.y]);
 }
 
+// v -> hi = bf16(v), lo = bf16(v - hi): operand pieces of the bf16x3 products (fp32 modules)
+__global__ void split_bf16x2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2bfloat16(f[j]);
+      l[j] = __float2bfloat16(f[j] - __bfloat162float(h[j]));
+    }
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_bf16x2(__bfloat162float(h[0]), __bfloat162float(h[1])),
+                                                 pack_bf16x2(__bfloat162float(h[2]), __bfloat162float(h[3])));
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack_bf16x2(__bfloat162float(l[0]), __bfloat162float(l[1])),
+                                                 pack_bf16x2(__bfloat162float(l[2]), __bfloat162float(l[3])));
+  }
+}
+__global__ void split_bf16x2_tail_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int64_t begin, int64_t n) {
+  const int64_t i = begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    const __nv_bfloat16 h = __float2bfloat16(src[i]);
+    hi[i] = h;
+    lo[i] = __float2bfloat16(src[i] - __bfloat162float(h));
+  }
+}
+
 // dbias[o] = sum_t dY[t, o]: block = 64 columns x 4 row-lanes, grid.y splits T; every block writes its partial row,
 // the conversion kernel sums the partial rows in a fixed order (bit-reproducible).
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ part, int64_t T, int out) {
@@ -142,6 +171,9 @@ static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32
   if (EPI == EPI_BF16_TMA) {
     rc = make_tensor_map_2d(&maps.c, C_bf16, N, M, static_cast<uint64_t>(ldc) * 2, kStoreBoxCols, kBM, 2);
     if (rc) return rc;
+  } else if (EPI == EPI_F32_TMA) {
+    rc = make_tensor_map_2d(&maps.c, C_f32, N, M, static_cast<uint64_t>(ldc) * 4, 32, kBM, 4);
+    if (rc) return rc;
   }
   p.M = M;
   p.N = N;
@@ -160,7 +192,8 @@ static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32
   p.splits = ceil_div(kb_total, std::max(1, p.kb_per_split));
   p.alpha_blocks = (n_alpha > 1) ? std::min(n_alpha, kMaxAlphaBlocks) : 0;
   for (int i = 0; i < kMaxAlphaBlocks; ++i) p.alpha[i] = (i < n_alpha) ? alpha_blocks[i] : alpha_blocks[std::max(0, n_alpha - 1)];
-  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.bias = (EPI == EPI_BF16_TMA) ? static_cast<const __nv_bfloat16*>(bias) : nullptr;
+  p.bias_f32 = (EPI == EPI_F32_TMA) ? static_cast<const float*>(bias) : nullptr;
   p.out_f32 = C_f32;
   p.split_stride = static_cast<int64_t>(M) * ldc;
   p.ldc = ldc;
@@ -192,18 +225,18 @@ constexpr int kBiasParts = 64;
 static int skinny_bn(int R) { return R >= 256 ? 256 : R; }
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch_skinny(int R, const Segment* seg, void* C_bf16, float* C_f32, int ldc, int M, const float* alpha,
-                         int n_alpha, bool split_k, cudaStream_t stream, int prof_class, double alg_flops,
-                         int* splits_out = nullptr) {
+static int launch_skinny(int R, const Segment* seg, int nseg, void* C_bf16, float* C_f32, int ldc, int M,
+                         const float* alpha, int n_alpha, bool split_k, cudaStream_t stream, int prof_class,
+                         double alg_flops, int* splits_out = nullptr) {
   switch (skinny_bn(R)) {
     case 64:
-      return launch_gemm<64, A_MN, B_MN, EPI>(seg, 1, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
+      return launch_gemm<64, A_MN, B_MN, EPI>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
     case 128:
-      return launch_gemm<128, A_MN, B_MN, EPI>(seg, 1, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
+      return launch_gemm<128, A_MN, B_MN, EPI>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
     case 192:
-      return launch_gemm<192, A_MN, B_MN, EPI>(seg, 1, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
+      return launch_gemm<192, A_MN, B_MN, EPI>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
     default:
-      return launch_gemm<256, A_MN, B_MN, EPI>(seg, 1, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
+      return launch_gemm<256, A_MN, B_MN, EPI>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
   }
 }
 
@@ -267,8 +300,7 @@ static int group_layout(const char* fn, const sowb_group_member* m, int n, int64
     const int rc0 = ensure_context_for(any);   // backward runs on autograd's worker thread
     if (rc0) return rc0;
   }
-  if (dtype != SOWB_BF16)
-    return set_error(SOWB_EINVAL, "%s: only SOWB_BF16 is implemented on device (fp32 modules are split into bf16 pieces by the caller)", fn);
+  if (dtype != SOWB_BF16 && dtype != SOWB_F32) return set_error(SOWB_EINVAL, "%s: unknown dtype %d", fn, dtype);
   if (m == nullptr || n < 1 || n > kMaxGroup) return set_error(SOWB_EINVAL, "%s: group size %d (1..%d)", fn, n, kMaxGroup);
   if (T <= 0 || in <= 0) return set_error(SOWB_EINVAL, "%s: non-positive dimension", fn);
   if (T >= (int64_t(1) << 31)) return set_error(SOWB_EINVAL, "%s: T too large", fn);
@@ -340,12 +372,35 @@ size_t sow_group_workspace_bytes(int op, int64_t T, int in, const sowb_group_mem
   return group_bwd_ws(m, L, T, in, nullptr, nullptr, nullptr);
 }
 
-int sow_group_fwd(const void* x, const sowb_group_member* m, int n, void* A_cat, void* t_cat, int64_t T, int in,
-                  int dtype, void* stream_) {
+int sow_split_bf16x2(const float* src, void* hi, void* lo, int64_t n, void* stream_) {
+  if (n <= 0) return SOWB_OK;
+  SOWB_REQUIRE(src && hi && lo, "sow_split_bf16x2: null pointer argument");
+  if (int rc0 = ensure_context_for(src)) return rc0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(lo) & 7) == 0) ? n / 4 : 0;
+  if (n4 > 0) {
+    const int blocks = static_cast<int>(std::min<int64_t>((n4 + 255) / 256, int64_t(num_sms()) * 16));
+    split_bf16x2_kernel<<<blocks, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n4);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (n4 * 4 < n) {
+    const int64_t rem = n - n4 * 4;
+    split_bf16x2_tail_kernel<<<static_cast<int>((rem + 255) / 256), 256, 0, stream>>>(
+        src, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n4 * 4, n);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+  }
+  return SOWB_OK;
+}
+
+int sow_group_fwd(const void* x, const void* x_lo, const sowb_group_member* m, int n, void* A_cat, void* t_cat, int64_t T,
+                  int in, int dtype, void* stream_) {
   GroupLayout L;
   int rc = group_layout("sow_group_fwd", m, n, T, in, dtype, x, &L);
   if (rc) return rc;
   SOWB_REQUIRE(x && A_cat && t_cat, "sow_group_fwd: null pointer argument");
+  const bool f32 = dtype == SOWB_F32;
+  SOWB_REQUIRE(!f32 || x_lo != nullptr, "sow_group_fwd: SOWB_F32 needs the low piece of x");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int R = L.R;
   {
@@ -369,12 +424,14 @@ int sow_group_fwd(const void* x, const sowb_group_member* m, int n, void* A_cat,
     int nb = 0;
     for (int i = 0; i < n; ++i)
       for (int b = 0; b < L.rpad[i] / 64; ++b) alpha[nb++] = m[i].scale;
-    Segment sg{Operand{x, uint64_t(T), uint64_t(in), uint64_t(in)},
-               Operand{A_cat, uint64_t(in), uint64_t(R), uint64_t(R)}, in};   // B operand [K=in rows, N=R cols]
+    Segment sg[2] = {{Operand{x, uint64_t(T), uint64_t(in), uint64_t(in)},
+                      Operand{A_cat, uint64_t(in), uint64_t(R), uint64_t(R)}, in},   // B operand [K=in rows, N=R cols]
+                     {Operand{x_lo, uint64_t(T), uint64_t(in), uint64_t(in)},
+                      Operand{A_cat, uint64_t(in), uint64_t(R), uint64_t(R)}, in}};
     int rsum = 0;
     for (int i = 0; i < n; ++i) rsum += m[i].r;
-    rc = launch_skinny<false, true, EPI_BF16_TMA>(R, &sg, t_cat, nullptr, R, static_cast<int>(T), alpha, nb, false, stream,
-                                                  PROF_GEMM_SKINNY, 2.0 * double(T) * double(in) * double(rsum));
+    rc = launch_skinny<false, true, EPI_BF16_TMA>(R, sg, f32 ? 2 : 1, t_cat, nullptr, R, static_cast<int>(T), alpha, nb, false,
+                                                  stream, PROF_GEMM_SKINNY, 2.0 * double(T) * double(in) * double(rsum));
     if (rc) return rc;
   }
   // y_i = x . W_i + t_i . B_i (+ bias_i)
@@ -382,18 +439,31 @@ int sow_group_fwd(const void* x, const sowb_group_member* m, int n, void* A_cat,
   for (int i = 0; i < n; ++i) {
     SOWB_REQUIRE(m[i].y != nullptr, "sow_group_fwd: member %d has no output buffer", i);
     const __nv_bfloat16* t_i = static_cast<const __nv_bfloat16*>(t_cat) + L.off[i];
-    Segment segs[2];
+    Segment segs[4];
     int ns = 0;
-    if (m[i].W != nullptr)
-      segs[ns++] = Segment{Operand{x, uint64_t(T), uint64_t(in), uint64_t(in)},
-                           Operand{m[i].W, uint64_t(in), uint64_t(m[i].out), uint64_t(m[i].out)}, in};
+    if (m[i].W != nullptr) {
+      const Operand opX{x, uint64_t(T), uint64_t(in), uint64_t(in)};
+      const Operand opW{m[i].W, uint64_t(in), uint64_t(m[i].out), uint64_t(m[i].out)};
+      segs[ns++] = Segment{opX, opW, in};
+      if (f32) {
+        SOWB_REQUIRE(m[i].W_lo != nullptr, "sow_group_fwd: SOWB_F32 needs the low piece of W (member %d)", i);
+        const Operand opXl{x_lo, uint64_t(T), uint64_t(in), uint64_t(in)};
+        const Operand opWl{m[i].W_lo, uint64_t(in), uint64_t(m[i].out), uint64_t(m[i].out)};
+        segs[ns++] = Segment{opX, opWl, in};
+        segs[ns++] = Segment{opXl, opW, in};
+      }
+    }
     // rows >= r of B read as zero through the tensor-map bounds
     segs[ns++] = Segment{Operand{t_i, uint64_t(T), uint64_t(L.rpad[i]), uint64_t(R)},
                          Operand{m[i].B, uint64_t(m[i].r), uint64_t(m[i].out), uint64_t(m[i].out)}, L.rpad[i]};
-    rc = launch_gemm<256, false, true, EPI_BF16_TMA>(segs, ns, m[i].y, nullptr, m[i].out, static_cast<int>(T), m[i].out,
-                                                     &one, 1, m[i].bias, false, stream, PROF_GEMM_FWD,
-                                                     2.0 * double(T) * double(m[i].out) *
-                                                         (double(m[i].W != nullptr ? in : 0) + double(m[i].r)));
+    const double fl = 2.0 * double(T) * double(m[i].out) * (double(m[i].W != nullptr ? in : 0) + double(m[i].r));
+    if (f32)
+      rc = launch_gemm<256, false, true, EPI_F32_TMA>(segs, ns, nullptr, static_cast<float*>(m[i].y), m[i].out,
+                                                      static_cast<int>(T), m[i].out, &one, 1, m[i].bias, false, stream,
+                                                      PROF_GEMM_FWD, fl);
+    else
+      rc = launch_gemm<256, false, true, EPI_BF16_TMA>(segs, ns, m[i].y, nullptr, m[i].out, static_cast<int>(T), m[i].out,
+                                                       &one, 1, m[i].bias, false, stream, PROF_GEMM_FWD, fl);
     if (rc) return rc;
   }
   return SOWB_OK;
@@ -512,7 +582,7 @@ int sow_group_bwd(const void* x, const void* A_cat, const void* t_cat, const sow
                Operand{dt_cat, uint64_t(T), uint64_t(R), uint64_t(R)}, Ti};  // B operand MN-major: [K=T rows, N=R cols]
     int rsum = 0;
     for (int i = 0; i < n; ++i) rsum += m[i].r;
-    rc = launch_skinny<true, true, EPI_F32_PARTIAL>(R, &sg, nullptr, partA, R, in, &one, 1, true, stream, PROF_GEMM_SPLITK,
+    rc = launch_skinny<true, true, EPI_F32_PARTIAL>(R, &sg, 1, nullptr, partA, R, in, &one, 1, true, stream, PROF_GEMM_SPLITK,
                                                     2.0 * double(T) * double(in) * double(rsum), &splitsA);
     if (rc) return rc;
     if (splitsA > splitk_count(in, R, skinny_bn(R), Ti))
@@ -590,23 +660,33 @@ int sow_group_bwd(const void* x, const void* A_cat, const void* t_cat, const sow
     Segment segs[kMaxSeg];
     int ns = 0;
     // W (in,out) is K-major for this product: [N=in rows, K=out cols]
-    auto w_seg = [&](int i) {
-      return Segment{Operand{m[i].dy, uint64_t(T), uint64_t(m[i].out), uint64_t(m[i].out)},
-                     Operand{m[i].W, uint64_t(in), uint64_t(m[i].out), uint64_t(m[i].out)}, m[i].out};
-    };
+    const bool f32 = dtype == SOWB_F32;
     Segment tail{Operand{dt_cat, uint64_t(T), uint64_t(R), uint64_t(R)},
                  Operand{A_cat, uint64_t(in), uint64_t(R), uint64_t(R)}, R};   // [N=in rows, K=R cols]
     int nW = 0;
     for (int i = 0; i < n; ++i) nW += m[i].W != nullptr;
-    if (nW + 1 > kMaxSeg)
-      return set_error(SOWB_EINVAL, "sow_group_bwd: %d members with a dense W exceed one dX launch (max %d)", nW, kMaxSeg - 1);
-    for (int i = 0; i < n; ++i)
-      if (m[i].W != nullptr) segs[ns++] = w_seg(i);
+    if (nW * (f32 ? 3 : 1) + 1 > kMaxSeg)
+      return set_error(SOWB_EINVAL, "sow_group_bwd: %d members with a dense W exceed one dX launch", nW);
+    for (int i = 0; i < n; ++i) {
+      if (m[i].W == nullptr) continue;
+      const Operand opDY{m[i].dy, uint64_t(T), uint64_t(m[i].out), uint64_t(m[i].out)};
+      const Operand opW{m[i].W, uint64_t(in), uint64_t(m[i].out), uint64_t(m[i].out)};
+      segs[ns++] = Segment{opDY, opW, m[i].out};
+      if (f32) {
+        SOWB_REQUIRE(m[i].W_lo && m[i].dy_lo, "sow_group_bwd: SOWB_F32 needs the low pieces of W and dY (member %d)", i);
+        segs[ns++] = Segment{opDY, Operand{m[i].W_lo, uint64_t(in), uint64_t(m[i].out), uint64_t(m[i].out)}, m[i].out};
+        segs[ns++] = Segment{Operand{m[i].dy_lo, uint64_t(T), uint64_t(m[i].out), uint64_t(m[i].out)}, opW, m[i].out};
+      }
+    }
     segs[ns++] = tail;
     double kalg = 0;
     for (int i = 0; i < n; ++i) kalg += double(m[i].W != nullptr ? m[i].out : 0) + double(m[i].r);
-    rc = launch_gemm<256, false, false, EPI_BF16_TMA>(segs, ns, dx, nullptr, in, Ti, in, &one, 1, nullptr, false, stream,
-                                                      PROF_GEMM_DX, 2.0 * double(T) * double(in) * kalg);
+    if (f32)
+      rc = launch_gemm<256, false, false, EPI_F32_TMA>(segs, ns, nullptr, static_cast<float*>(dx), in, Ti, in, &one, 1, nullptr,
+                                                       false, stream, PROF_GEMM_DX, 2.0 * double(T) * double(in) * kalg);
+    else
+      rc = launch_gemm<256, false, false, EPI_BF16_TMA>(segs, ns, dx, nullptr, in, Ti, in, &one, 1, nullptr, false, stream,
+                                                        PROF_GEMM_DX, 2.0 * double(T) * double(in) * kalg);
     if (rc) return rc;
   }
   return SOWB_OK;

@@ -532,6 +532,93 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
   if (warp == 9) tmem_dealloc(tmem_base, kMgTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 variant (fp32 modules: the reference's GLUE fine-tunes keep W, A, B in fp32, run_glue.py:386-388; sow.py:131-153
+// then accumulates in fp32).  Exact fp32 FMA on the CUDA cores: 2r flop per 8 bytes is far below the fp32 roof at the
+// ranks those configs use (r = 8), and the merged W matches an fp32 evaluation to rounding -- a bf16 tensor-core product
+// would cost the pretrained weights 16 mantissa bits at every merge.  One launch for all matrices: 32 x 128 tiles,
+// thread = 4 rows x 4 columns (float4), A / B tiles staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct MergeF32Entry {
+  float* W;
+  const float* W_prev;   // nullptr: first merge
+  const float* A;        // (in, r)
+  const float* B;        // (r, out)
+  int in, out, r;
+  float scale;
+  int n_tiles;           // column tiles of 128
+  int tile_begin;
+};
+constexpr int kMfBM = 32, kMfBN = 128, kMfMaxR = 64;
+
+__global__ void __launch_bounds__(256)
+sow_merge_f32_kernel(const MergeF32Entry* __restrict__ tab, int n_entries, int total_tiles) {
+  __shared__ float sA[kMfBM][kMfMaxR + 1];
+  __shared__ __align__(16) float sB[kMfMaxR][kMfBN];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // tx: float4 column group, ty: 4-row group
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tab[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    const MergeF32Entry e = tab[lo];
+    const int local = tile - e.tile_begin;
+    const int m0 = (local / e.n_tiles) * kMfBM, n0 = (local % e.n_tiles) * kMfBN;
+    for (int r0 = 0; r0 < e.r; r0 += kMfMaxR) {
+      const int rc = min(kMfMaxR, e.r - r0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < kMfBM * rc; i += 256) {
+        const int row = i / rc, k = i % rc;
+        sA[row][k] = (m0 + row < e.in) ? e.A[static_cast<int64_t>(m0 + row) * e.r + r0 + k] : 0.f;
+      }
+      for (int i = threadIdx.x; i < rc * kMfBN; i += 256) {
+        const int k = i / kMfBN, col = i % kMfBN;
+        sB[k][col] = (n0 + col < e.out) ? e.B[static_cast<int64_t>(r0 + k) * e.out + n0 + col] : 0.f;
+      }
+      __syncthreads();
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int k = 0; k < rc; ++k) {
+        const float4 b = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = sA[ty * 4 + i][k];
+          acc[i][0] = fmaf(a, b.x, acc[i][0]);
+          acc[i][1] = fmaf(a, b.y, acc[i][1]);
+          acc[i][2] = fmaf(a, b.z, acc[i][2]);
+          acc[i][3] = fmaf(a, b.w, acc[i][3]);
+        }
+      }
+      const int col = n0 + tx * 4;
+      const bool vec = (e.out & 3) == 0 && col + 3 < e.out;
+      const float* prev = (r0 == 0) ? e.W_prev : e.W;       // later rank chunks accumulate onto what this launch wrote
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = m0 + ty * 4 + i;
+        if (row >= e.in) continue;
+        const int64_t off = static_cast<int64_t>(row) * e.out + col;
+        if (vec) {
+          float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (prev != nullptr) w = *reinterpret_cast<const float4*>(prev + off);
+          w.x = fmaf(e.scale, acc[i][0], w.x);
+          w.y = fmaf(e.scale, acc[i][1], w.y);
+          w.z = fmaf(e.scale, acc[i][2], w.z);
+          w.w = fmaf(e.scale, acc[i][3], w.w);
+          *reinterpret_cast<float4*>(e.W + off) = w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col + j < e.out) e.W[off + j] = fmaf(e.scale, acc[i][j], prev != nullptr ? prev[off + j] : 0.f);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace sowb
 
 using namespace sowb;
@@ -549,15 +636,53 @@ int sow_merge_debug_timeline(void* buf) {
 
 size_t sow_merge_table_stride(void) {
   // one device entry per 64-wide rank chunk; callers size the table for ceil(r/64) chunks per layer
+  static_assert(sizeof(MergeF32Entry) <= sizeof(MergeDevEntry), "the fp32 table fits the same stride");
   return sizeof(MergeDevEntry);
+}
+
+static int merge_grouped_f32(const sowb_merge_entry* entries, int n, void* table_dev, size_t table_bytes, cudaStream_t stream) {
+  if (table_bytes < size_t(n) * sizeof(MergeF32Entry))
+    return set_error(SOWB_EWORKSPACE, "sow_merge_grouped: table %zu B < required %zu B", table_bytes, size_t(n) * sizeof(MergeF32Entry));
+  std::vector<MergeF32Entry> host(n);
+  int tiles = 0;
+  double bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    const sowb_merge_entry& e = entries[i];
+    SOWB_REQUIRE(e.W && e.A && e.B, "sow_merge_grouped: entry %d has a null W/A/B pointer", i);
+    SOWB_REQUIRE(e.in > 0 && e.out > 0 && e.r > 0, "sow_merge_grouped: entry %d has a non-positive dimension", i);
+    MergeF32Entry& d = host[i];
+    d.W = static_cast<float*>(e.W);
+    d.W_prev = static_cast<const float*>(e.W_prev);
+    d.A = static_cast<const float*>(e.A);
+    d.B = static_cast<const float*>(e.B);
+    d.in = e.in;
+    d.out = e.out;
+    d.r = e.r;
+    d.scale = e.scale;
+    d.n_tiles = ceil_div(e.out, kMfBN);
+    d.tile_begin = tiles;
+    tiles += ceil_div(e.in, kMfBM) * d.n_tiles;
+    bytes += 4.0 * e.in * e.out * (1 + (e.W_prev != nullptr)) + 4.0 * e.r * (double(e.in) + e.out);
+  }
+  SOWB_CHECK_CUDA(cudaMemcpyAsync(table_dev, host.data(), size_t(n) * sizeof(MergeF32Entry), cudaMemcpyHostToDevice, stream));
+  const int grid = std::min(tiles, num_sms() * 8);
+  ProfileScope prof(stream, PROF_MERGE, bytes);
+  sow_merge_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const MergeF32Entry*>(table_dev), n, tiles);
+  SOWB_CHECK_CUDA(cudaGetLastError());
+  return SOWB_OK;
 }
 
 int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* table_dev, size_t table_bytes,
                       void* stream_) {
   if (n <= 0) return SOWB_OK;
-  if (dtype != SOWB_BF16) return set_error(SOWB_EINVAL, "sow_merge_grouped: only SOWB_BF16 is implemented");
+  if (dtype != SOWB_BF16 && dtype != SOWB_F32) return set_error(SOWB_EINVAL, "sow_merge_grouped: unknown dtype %d", dtype);
   SOWB_REQUIRE(entries != nullptr && table_dev != nullptr, "sow_merge_grouped: null pointer argument");
   if (int rc0 = ensure_context_for(table_dev)) return rc0;
+  if (dtype == SOWB_F32) {
+    int rcf = require_sm100();
+    if (rcf) return rcf;
+    return merge_grouped_f32(entries, n, table_dev, table_bytes, static_cast<cudaStream_t>(stream_));
+  }
   SOWB_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 127) == 0, "sow_merge_grouped: table_dev must be 128-byte aligned");
   int rc = require_sm100();
   if (rc) return rc;

@@ -79,15 +79,18 @@ class _SoWGroupFn(torch.autograd.Function):
     """y_i = x.W_i + scale_i*(x.A_i).B_i + bias_i for the n projections of a group that read the same x, W_i frozen.
     Saves x, the packed factors A_cat and t_cat = scale_i*x.A_cat (T x R); never forms dW.
 
-    Positional inputs after ``scales``: for each member (W_c or None, A, B, bias or None).  Inputs of other dtypes follow
-    the bf16 compute policy: cast to bf16 on the way in, results cast back to the caller's dtype.  ``W_c`` is
-    the bf16 compute copy of W (W itself when W is bf16)."""
+    Positional inputs after ``scales``: for each member (W_c or None, A, B, bias or None, W_lo or None).
+      * bf16 modules: ``W_c`` is W itself, everything runs in bf16 with fp32 accumulation.
+      * fp32 modules (fp32 x, and every dense W given as its two bf16 pieces W_c + W_lo, see SoWLinear._compute_weight):
+        the fp32-faithful path -- x and dY are split into two bf16 pieces on the fly, the base products run as bf16x3
+        tensor-core contractions, outputs and dX are fp32; the small rank-r factors are rounded to bf16 once.
+      * anything else (mixed dtypes) follows the bf16 compute policy: cast in, cast back."""
 
     @staticmethod
     def forward(ctx, x, scales, *params):
         n = len(scales)
         out_dtype = x.dtype
-        Ws, As, Bs, biases = params[0::4], params[1::4], params[2::4], params[3::4]
+        Ws, As, Bs, biases, Wlos = params[0::5], params[1::5], params[2::5], params[3::5], params[4::5]
         fin = As[0].shape[0]
         lead = x.shape[:-1]
         ctx.n = n
@@ -98,12 +101,25 @@ class _SoWGroupFn(torch.autograd.Function):
             ctx.empty = True
             return tuple(x.new_zeros(*lead, b.shape[1]) for b in Bs)
         ctx.empty = False
-        x2 = _bf16c(x.reshape(-1, fin))
-        Wc = [_bf16c(w) for w in Ws]
+        f32 = (x.dtype == torch.float32 and all((w is None) == (wl is None) for w, wl in zip(Ws, Wlos))
+               and all(b is None or b.dtype == torch.float32 for b in biases) and any(w is not None for w in Ws))
+        ctx.f32 = f32
         Bc = [_bf16c(b) for b in Bs]
-        ys, A_cat, t_cat = ops.group_fwd(
-            x2, [(Wc[i], _bf16c(As[i]), Bc[i], _bf16c(biases[i]), scales[i]) for i in range(n)])
-        ctx.save_for_backward(x2, A_cat, t_cat, *Wc, *Bc)
+        if f32:
+            xf = x.reshape(-1, fin)
+            x2, x_lo = ops.split_f32(xf if xf.is_contiguous() else xf.contiguous())
+            Wc, Wl = list(Ws), list(Wlos)
+            ys, A_cat, t_cat = ops.group_fwd(
+                x2, [(Wc[i], _bf16c(As[i]), Bc[i], None if biases[i] is None else biases[i].contiguous(), scales[i], Wl[i])
+                     for i in range(n)], x_lo=x_lo)
+        else:
+            x2 = _bf16c(x.reshape(-1, fin))
+            Wc = [_bf16c(w) for w in Ws]
+            Wl = [None] * n
+            ys, A_cat, t_cat = ops.group_fwd(
+                x2, [(Wc[i], _bf16c(As[i]), Bc[i], _bf16c(biases[i]), scales[i]) for i in range(n)])
+        ctx.has_w = [w is not None for w in Wc]
+        ctx.save_for_backward(x2, A_cat, t_cat, *[w for w in Wc if w is not None], *[w for w in Wl if w is not None], *Bc)
         ctx.scales = tuple(float(s) for s in scales)
         # leaf factor Parameters: their gradients may be written straight into a flat bucket view
         ctx.leaves = [(a if isinstance(a, nn.Parameter) else None, b if isinstance(b, nn.Parameter) else None)
@@ -111,7 +127,7 @@ class _SoWGroupFn(torch.autograd.Function):
         outs = []
         for y, b in zip(ys, Bs):
             y = y.reshape(*lead, b.shape[1])
-            outs.append(y if out_dtype == torch.bfloat16 else y.to(out_dtype))
+            outs.append(y if y.dtype == out_dtype else y.to(out_dtype))
         return tuple(outs)
 
     @staticmethod
@@ -123,28 +139,40 @@ class _SoWGroupFn(torch.autograd.Function):
         grads = [None, None]
         if ctx.empty:
             for i in range(n):
-                nW, nA, nB, nb = need[2 + 4 * i: 6 + 4 * i]
+                nW, nA, nB, nb, _ = need[2 + 5 * i: 7 + 5 * i]
                 grads += [None,
                           torch.zeros(a_shapes[i], dtype=a_dts[i], device=dys[0].device) if nA else None,
                           torch.zeros(b_shapes[i], dtype=b_dts[i], device=dys[0].device) if nB else None,
-                          torch.zeros(b_shapes[i][1], dtype=bias_dts[i], device=dys[0].device) if (nb and bias_dts[i] is not None) else None]
+                          torch.zeros(b_shapes[i][1], dtype=bias_dts[i], device=dys[0].device) if (nb and bias_dts[i] is not None) else None,
+                          None]
             grads[0] = dys[0].new_zeros(*lead, fin) if need_x else None
             return tuple(grads)
-        saved = ctx.saved_tensors
+        saved = list(ctx.saved_tensors)
         x2, A_cat, t_cat = saved[0], saved[1], saved[2]
-        Wc, Bc = saved[3:3 + n], saved[3 + n:3 + 2 * n]
+        nw = sum(ctx.has_w)
+        w_it = iter(saved[3:3 + nw])
+        wl_it = iter(saved[3 + nw:3 + 2 * nw]) if ctx.f32 else iter(())
+        Bc = saved[-n:]
+        Wc = [next(w_it) if h else None for h in ctx.has_w]
+        Wl = [(next(wl_it) if h else None) if ctx.f32 else None for h in ctx.has_w]
         members = []
         for i in range(n):
-            nW, nA, nB, nb = need[2 + 4 * i: 6 + 4 * i]
-            dy2 = _bf16c(dys[i].reshape(-1, dys[i].shape[-1]))
+            nW, nA, nB, nb, _ = need[2 + 5 * i: 7 + 5 * i]
+            dyi = dys[i].reshape(-1, dys[i].shape[-1])
+            if ctx.f32:
+                dyi = dyi if dyi.dtype == torch.float32 else dyi.float()
+                dy2, dy_lo = ops.split_f32(dyi if dyi.is_contiguous() else dyi.contiguous())
+            else:
+                dy2, dy_lo = _bf16c(dyi), None
             pa, pb = ctx.leaves[i]
             dA_dst = (_grad_dst(pa) if a_dts[i] == torch.bfloat16 else True) if nA else None
             dB_dst = (_grad_dst(pb) if b_dts[i] == torch.bfloat16 else True) if nB else None
-            members.append((Wc[i], Bc[i], dy2, ctx.scales[i], dA_dst, dB_dst, bool(nb) and bias_dts[i] is not None))
-        dx, dAs, dBs, dbs = ops.group_bwd(x2, A_cat, t_cat, members, bool(need_x))
+            members.append((Wc[i], Bc[i], dy2, ctx.scales[i], dA_dst, dB_dst, bool(nb) and bias_dts[i] is not None,
+                            Wl[i], dy_lo if Wc[i] is not None else None))
+        dx, dAs, dBs, dbs = ops.group_bwd(x2, A_cat, t_cat, members, bool(need_x), f32=ctx.f32)
         if dx is not None:
             dx = dx.reshape(*lead, fin)
-            if out_dtype != torch.bfloat16:
+            if dx.dtype != out_dtype:
                 dx = dx.to(out_dtype)
         grads[0] = dx
         for i in range(n):
@@ -152,7 +180,8 @@ class _SoWGroupFn(torch.autograd.Function):
             grads += [None,
                       None if dA is None else (dA if a_dts[i] == torch.bfloat16 else dA.to(a_dts[i])),
                       None if dB is None else (dB if b_dts[i] == torch.bfloat16 else dB.to(b_dts[i])),
-                      None if db is None else (db if bias_dts[i] == torch.bfloat16 else db.to(bias_dts[i]))]
+                      None if db is None else (db if bias_dts[i] == torch.bfloat16 else db.to(bias_dts[i])),
+                      None]
         return tuple(grads)
 
 
@@ -163,9 +192,9 @@ def sow_linear_group(x, scales, params):
     return _SoWGroupFn.apply(x, tuple(scales), *params)
 
 
-def sow_linear(x, W_c, A, B, bias, scale):
+def sow_linear(x, W_c, A, B, bias, scale, W_lo=None):
     """One projection = a group of one."""
-    return sow_linear_group(x, (scale,), (W_c, A, B, bias))[0]
+    return sow_linear_group(x, (scale,), (W_c, A, B, bias, W_lo))[0]
 
 
 class SharedInputGroup:
@@ -227,7 +256,8 @@ def _forward_modules(mods: Sequence["SoWLinear"], x: torch.Tensor):
             # sum_i (x.A_i).B_i == (x.[A_1|..|A_n]).[B_1;..;B_n]: one fused call; autograd splits the grads
             A = torch.cat(A_list, dim=1)
             B = torch.cat(B_list, dim=0)
-        params += [m._compute_weight(), A, B, m.bias]
+        W_c, W_lo = m._compute_weight()
+        params += [W_c, A, B, m.bias, W_lo]
         scales.append(m.scale)
     return sow_linear_group(x, scales, params)
 
@@ -311,15 +341,22 @@ class SoWLinear(nn.Module):
             nn.init.zeros_(self.bias)
 
     # ---- forward (sow.py:107-126) ---------------------------------------------------------------------------
-    def _compute_weight(self) -> Optional[torch.Tensor]:
+    def _compute_weight(self):
+        """(W_c, W_lo): the operand(s) the kernels read for the frozen accumulation.  bf16 W: (W, None), no copy.  fp32 W:
+        its two bf16 pieces (W ~ W_c + W_lo, 2^-17 relative) for the bf16x3 path, cached until W changes (merge, load).
+        Other dtypes: one bf16 copy (bf16 compute policy)."""
         W = self.acc_downweight
         if W.numel() == 0:
-            return None
+            return None, None
         if W.dtype == torch.bfloat16 and W.is_contiguous():
-            return W
+            return W, None
         key = (W.data_ptr(), W._version, W.dtype)
         if self._w_shadow is None or self._w_shadow_key != key:
-            self._w_shadow = W.detach().to(torch.bfloat16).contiguous()
+            Wd = W.detach()
+            if W.dtype == torch.float32 and W.is_cuda:
+                self._w_shadow = ops.split_f32(Wd if Wd.is_contiguous() else Wd.contiguous())
+            else:
+                self._w_shadow = (Wd.to(torch.bfloat16).contiguous(), None)
             self._w_shadow_key = key
         return self._w_shadow
 
@@ -357,8 +394,12 @@ class SoWLinear(nn.Module):
 # ---------------------------------------------------------------------------------------------------------
 
 def _merge_dense(mods: List[SoWLinear]) -> None:
-    """Dense branch (sow.py:151-153) for all modules in one grouped launch per rank chunk."""
-    items = []
+    """Dense branch (sow.py:151-153) for all modules: one grouped launch per dtype class (and per 64-wide rank chunk).
+
+    bf16 modules: tcgen05 kernel, W updated IN PLACE (pointer-stable).  fp32 modules: exact fp32 kernel, in place -- the
+    pretrained weights keep their full precision, as in the reference (sow.py:131-153 stays in the parameter dtype).
+    Anything else (mixed dtypes, other devices) goes through a bf16 compute copy and is cast back."""
+    items = {torch.bfloat16: [], torch.float32: []}
     post = []
     for mod in mods:
         A_list = [a.detach() for a in mod.downscale_weights]
@@ -369,30 +410,40 @@ def _merge_dense(mods: List[SoWLinear]) -> None:
         A = A_list[0] if len(A_list) == 1 else torch.cat(A_list, dim=1)
         B = B_list[0] if len(B_list) == 1 else torch.cat(B_list, dim=0)
         pdtype = A.dtype
-        A_c, B_c = _bf16c(A), _bf16c(B)
         W_old = mod.acc_downweight
         expanded = W_old.numel() != 0 and mod.acc_upweight.numel() != 0
         if expanded:
             # last QR-growth step reached full rank: expand the factored accumulation once (sow.py:137-138); the
             # product is a temporary, so the merged result must be bound as the new acc_downweight below
             tgt = W_old.dtype
-            W_tmp = _bf16c((W_old.detach() @ mod.acc_upweight.detach()).to(dev))
-            items.append((W_tmp, W_tmp, A_c, B_c, mod.scale))
+            W_tmp = (W_old.detach() @ mod.acc_upweight.detach()).to(dev)
+            cls = torch.float32 if (tgt == torch.float32 and pdtype == torch.float32) else torch.bfloat16
+            W_tmp = W_tmp.to(cls).contiguous()
+            items[cls].append((W_tmp, W_tmp, A.to(cls).contiguous(), B.to(cls).contiguous(), mod.scale))
             post.append((mod, W_tmp, tgt))
             continue
         has_prev = W_old.numel() != 0
-        if has_prev and W_old.dtype == torch.bfloat16 and W_old.is_contiguous() and W_old.device == dev:
-            items.append((W_old.data, W_old.data, A_c, B_c, mod.scale))      # in-place RMW: pointer stays stable
-            post.append((mod, None, None))
+        wdt = W_old.dtype if has_prev else pdtype
+        native = wdt in items and pdtype == wdt and (not has_prev or (W_old.is_contiguous() and W_old.device == dev))
+        if native:
+            A_c, B_c = A.contiguous(), B.contiguous()
+            if has_prev:
+                items[wdt].append((W_old.data, W_old.data, A_c, B_c, mod.scale))      # in-place RMW: pointer stays stable
+                post.append((mod, None, None))
+            else:
+                W_new = torch.empty((mod.in_features, mod.out_features), dtype=wdt, device=dev)
+                items[wdt].append((W_new, None, A_c, B_c, mod.scale))
+                post.append((mod, W_new, wdt))
         else:
             W_new = torch.empty((mod.in_features, mod.out_features), dtype=torch.bfloat16, device=dev)
             prev = _bf16c(W_old.detach().to(dev)) if has_prev else None
-            items.append((W_new, prev, A_c, B_c, mod.scale))
-            post.append((mod, W_new, W_old.dtype if has_prev else pdtype))
-    ops.merge_grouped(items)
+            items[torch.bfloat16].append((W_new, prev, _bf16c(A), _bf16c(B), mod.scale))
+            post.append((mod, W_new, wdt))
+    for lst in items.values():
+        ops.merge_grouped(lst)
     for mod, W_new, tgt_dtype in post:
         if W_new is not None:
-            W_final = W_new if tgt_dtype == torch.bfloat16 else W_new.to(tgt_dtype)
+            W_final = W_new if tgt_dtype == W_new.dtype else W_new.to(tgt_dtype)
             mod.acc_downweight = nn.Parameter(W_final, requires_grad=False)
             mod.acc_upweight = nn.Parameter(torch.empty(0, device=W_final.device), requires_grad=False)
         mod._w_shadow = None

@@ -76,44 +76,72 @@ def _check_bf16c(name: str, t: Optional[torch.Tensor]):
         raise SowB200Error(f"{name} must be a contiguous bf16 tensor")
 
 
-def group_fwd(x: torch.Tensor, members: Sequence[Tuple[Optional[torch.Tensor], torch.Tensor, torch.Tensor,
-                                                       Optional[torch.Tensor], float]]):
+def split_f32(t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 tensor -> (hi, lo) bf16 pieces with t ~ hi + lo (relative error 2^-17): the operands of the bf16x3 tensor-core
+    products that give fp32 modules an fp32-faithful path (include/sow_b200.h: sow_split_bf16x2)."""
+    _require_cuda(t)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise SowB200Error("split_f32 expects a contiguous fp32 tensor")
+    hi = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    lo = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    check(_lib.load().sow_split_bf16x2(_p(t), _p(hi), _p(lo), t.numel(), _stream_ptr(t.device)), "sow_split_bf16x2")
+    launch_counter["kernels"] += 1
+    return hi, lo
+
+
+def group_fwd(x: torch.Tensor, members, x_lo: Optional[torch.Tensor] = None):
     """Forward of a group of SoW projections that read the same x (T,in) bf16 contiguous (include/sow_b200.h:
-    sow_group_fwd).  members: (W (in,out) or None, A (in,r), B (r,out), bias or None, scale).
-    Returns ([y_i (T,out_i)], A_cat (in,R), t_cat (T,R)); A_cat / t_cat are what autograd saves for group_bwd."""
+    sow_group_fwd).  members: (W (in,out) or None, A (in,r), B (r,out), bias or None, scale[, W_lo]).
+    With ``x_lo`` (SOWB_F32 mode) x / x_lo and W / W_lo are the bf16 pieces of fp32 operands, bias is fp32 and the outputs
+    are fp32.  Returns ([y_i (T,out_i)], A_cat (in,R), t_cat (T,R)); A_cat / t_cat are what autograd saves for group_bwd."""
     lib = _lib.load()
     n = len(members)
     T, fin = x.shape
-    _require_cuda(x)
+    f32 = x_lo is not None
+    _require_cuda(x, x_lo)
     _check_bf16c("x", x)
+    _check_bf16c("x_lo", x_lo)
     arr = (_lib.GroupMember * n)()
     ys = []
     R = 0
-    for i, (W, A, B, bias, scale) in enumerate(members):
-        _require_cuda(W, A, B, bias)
-        for nm, t in (("W", W), ("A", A), ("B", B), ("bias", bias)):
+    keep = []
+    for i, mem in enumerate(members):
+        W, A, B, bias, scale = mem[:5]
+        W_lo = mem[5] if len(mem) > 5 else None
+        _require_cuda(W, A, B, bias, W_lo)
+        for nm, t in (("W", W), ("A", A), ("B", B), ("W_lo", W_lo)):
             _check_bf16c(nm, t)
+        if f32:
+            if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+                raise SowB200Error("group_fwd: fp32 mode needs a contiguous fp32 bias")
+            if (W is None) != (W_lo is None):
+                raise SowB200Error("group_fwd: fp32 mode needs both pieces of W")
+        else:
+            _check_bf16c("bias", bias)
         r, fout = B.shape
         if A.shape != (fin, r) or (W is not None and tuple(W.shape) != (fin, fout)):
             raise SowB200Error("group_fwd: shape mismatch")
-        y = torch.empty((T, fout), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((T, fout), dtype=torch.float32 if f32 else torch.bfloat16, device=x.device)
         ys.append(y)
-        arr[i].W, arr[i].A, arr[i].B, arr[i].bias = _p(W), _p(A), _p(B), _p(bias)
+        arr[i].W, arr[i].W_lo, arr[i].A, arr[i].B, arr[i].bias = _p(W), _p(W_lo), _p(A), _p(B), _p(bias)
         arr[i].y = _p(y)
         arr[i].out_features, arr[i].r, arr[i].scale = fout, r, float(scale)
         R += rank_pad(r)
+        keep.append((W, W_lo, A, B, bias))
     A_cat = torch.empty((fin, R), dtype=torch.bfloat16, device=x.device)
     t_cat = torch.empty((T, R), dtype=torch.bfloat16, device=x.device)
-    rc = lib.sow_group_fwd(_p(x), arr, n, _p(A_cat), _p(t_cat), T, fin, SOWB_BF16, _stream_ptr(x.device))
+    rc = lib.sow_group_fwd(_p(x), _p(x_lo), arr, n, _p(A_cat), _p(t_cat), T, fin, SOWB_F32 if f32 else SOWB_BF16,
+                           _stream_ptr(x.device))
     check(rc, "sow_group_fwd")
     launch_counter["kernels"] += 2 + n
     return ys, A_cat, t_cat
 
 
-def group_bwd(x: torch.Tensor, A_cat: torch.Tensor, t_cat: torch.Tensor, members, need_dx: bool):
+def group_bwd(x: torch.Tensor, A_cat: torch.Tensor, t_cat: torch.Tensor, members, need_dx: bool, f32: bool = False):
     """Backward of a group (sow_group_bwd).  members: (W or None, B (r,out), dy (T,out), scale, dA_dst, dB_dst,
-    want_dbias) where dA_dst / dB_dst are None (not needed), True (allocate) or a preallocated contiguous bf16 tensor of
-    the gradient's shape (e.g. a view into a flat gradient bucket) that the kernels write in place.
+    want_dbias[, W_lo, dy_lo]) where dA_dst / dB_dst are None (not needed), True (allocate) or a preallocated contiguous
+    bf16 tensor of the gradient's shape (e.g. a view into a flat gradient bucket) that the kernels write in place.
+    ``f32``: W / W_lo and dy / dy_lo are bf16 pieces of fp32 operands and dx is fp32.
     Returns (dx or None, [dA_i], [dB_i], [dbias_i])."""
     lib = _lib.load()
     n = len(members)
@@ -123,11 +151,13 @@ def group_bwd(x: torch.Tensor, A_cat: torch.Tensor, t_cat: torch.Tensor, members
     arr = (_lib.GroupMember * n)()
     dAs, dBs, dbs = [], [], []
     keep = []
-    for i, (W, B, dy, scale, dA_dst, dB_dst, want_dbias) in enumerate(members):
-        _require_cuda(W, B, dy)
-        _check_bf16c("W", W)
-        _check_bf16c("B", B)
-        _check_bf16c("dy", dy)
+    for i, mem in enumerate(members):
+        W, B, dy, scale, dA_dst, dB_dst, want_dbias = mem[:7]
+        W_lo = mem[7] if len(mem) > 7 else None
+        dy_lo = mem[8] if len(mem) > 8 else None
+        _require_cuda(W, B, dy, W_lo, dy_lo)
+        for nm, t in (("W", W), ("B", B), ("dy", dy), ("W_lo", W_lo), ("dy_lo", dy_lo)):
+            _check_bf16c(nm, t)
         r, fout = B.shape
         if tuple(dy.shape) != (T, fout):
             raise SowB200Error("group_bwd: dy shape mismatch")
@@ -146,17 +176,17 @@ def group_bwd(x: torch.Tensor, A_cat: torch.Tensor, t_cat: torch.Tensor, members
         dAs.append(dA)
         dBs.append(dB)
         dbs.append(db)
-        arr[i].W, arr[i].B, arr[i].dy = _p(W), _p(B), _p(dy)
+        arr[i].W, arr[i].W_lo, arr[i].B, arr[i].dy, arr[i].dy_lo = _p(W), _p(W_lo), _p(B), _p(dy), _p(dy_lo)
         arr[i].A = _p(A_cat)       # not read by the backward (A_cat carries the factors); must be non-null
         arr[i].dA, arr[i].dB, arr[i].dbias = _p(dA), _p(dB), _p(db)
         arr[i].out_features, arr[i].r, arr[i].scale = fout, r, float(scale)
-        keep.append((W, B, dy))
+        keep.append((W, W_lo, B, dy, dy_lo))
     dt_cat = torch.empty((T, R), dtype=torch.bfloat16, device=dev)
-    dx = torch.empty((T, fin), dtype=torch.bfloat16, device=dev) if need_dx else None
+    dx = torch.empty((T, fin), dtype=torch.float32 if f32 else torch.bfloat16, device=dev) if need_dx else None
     nws = lib.sow_group_workspace_bytes(_lib.OP_LINEAR_BWD, T, fin, arr, n)
     ws = workspace(dev, nws)
-    rc = lib.sow_group_bwd(_p(x), _p(A_cat), _p(t_cat), arr, n, _p(dt_cat), _p(dx), T, fin, SOWB_BF16, _p(ws), ws.numel(),
-                           _stream_ptr(dev))
+    rc = lib.sow_group_bwd(_p(x), _p(A_cat), _p(t_cat), arr, n, _p(dt_cat), _p(dx), T, fin, SOWB_F32 if f32 else SOWB_BF16,
+                           _p(ws), ws.numel(), _stream_ptr(dev))
     check(rc, "sow_group_bwd")
     # K2 (one launch when the members share a cluster size, else n) + split-K dA + finalize + dX + colsum pairs
     uniform = len({(m[1].shape[1], rank_pad(m[1].shape[0])) for m in members}) == 1
@@ -183,19 +213,22 @@ def linear_bwd(dy, x, A_pad, t, W, B, scale: float, want_dbias: bool, need_dx: b
 # ---------------------------------------------------------------------------------------------------------
 
 def merge_grouped(items: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor, torch.Tensor, float]]):
-    """items: (W_out (in,out), W_prev or None, A (in,r), B (r,out), scale), all bf16 CUDA contiguous on one
-    device.  One launch per 64-wide rank chunk for the whole list."""
+    """items: (W_out (in,out), W_prev or None, A (in,r), B (r,out), scale), all CUDA contiguous on one device and all
+    of ONE dtype: bf16 (tcgen05 path, one launch per 64-wide rank chunk for the whole list) or fp32 (exact fp32 path)."""
     if not items:
         return
     lib = _lib.load()
     dev = items[0][0].device
     n = len(items)
+    dt = items[0][0].dtype
+    if dt not in (torch.bfloat16, torch.float32):
+        raise SowB200Error(f"merge_grouped: unsupported dtype {dt}")
     arr = (MergeEntry * n)()
     for i, (W, Wp, A, B, s) in enumerate(items):
         _require_cuda(W, Wp, A, B)
         for tname, tt in (("W", W), ("W_prev", Wp), ("A", A), ("B", B)):
-            if tt is not None and (tt.dtype != torch.bfloat16 or not tt.is_contiguous()):
-                raise SowB200Error(f"merge_grouped: {tname} must be a contiguous bf16 tensor")
+            if tt is not None and (tt.dtype != dt or not tt.is_contiguous()):
+                raise SowB200Error(f"merge_grouped: {tname} must be a contiguous {dt} tensor")
         fin, r = A.shape
         fout = B.shape[1]
         if tuple(W.shape) != (fin, fout) or B.shape[0] != r:
@@ -210,7 +243,7 @@ def merge_grouped(items: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], to
     table = workspace(dev, n * stride + 256)
     base = table.data_ptr()
     aligned = (base + 127) // 128 * 128
-    rc = lib.sow_merge_grouped(arr, n, SOWB_BF16, ctypes.c_void_p(aligned), table.numel() - (aligned - base),
+    rc = lib.sow_merge_grouped(arr, n, _dtype_code(dt), ctypes.c_void_p(aligned), table.numel() - (aligned - base),
                                _stream_ptr(dev))
     check(rc, "sow_merge_grouped")
     launch_counter["kernels"] += max((a[2].shape[1] + 63) // 64 for a in items)

@@ -24,15 +24,21 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-300))
 
 
-def _torch_sow_linear(x, W_c, A, B, bias, scale):
-    """sow.py:107-126 in fp32 torch ops (x.W + scale*(x.A).B + bias); same signature as sow_b200.layer.sow_linear."""
+def _torch_sow_linear_group(x, scales, params):
+    """sow.py:107-126 in fp32 torch ops (x.W + scale*(x.A).B + bias) for every member of a group; same signature as
+    sow_b200.layer.sow_linear_group (per member: W_c, A, B, bias, W_lo -- W = W_c + W_lo for fp32 modules)."""
     xf = x.float()
-    out = scale * ((xf @ A.float()) @ B.float())
-    if W_c is not None:
-        out = out + xf @ W_c.float()
-    if bias is not None:
-        out = out + bias.float()
-    return out.to(x.dtype)
+    outs = []
+    for i, scale in enumerate(scales):
+        W_c, A, B, bias, W_lo = params[5 * i:5 * i + 5]
+        out = scale * ((xf @ A.float()) @ B.float())
+        if W_c is not None:
+            W = W_c.float() if W_lo is None else W_c.float() + W_lo.float()
+            out = out + xf @ W
+        if bias is not None:
+            out = out + bias.float()
+        outs.append(out.to(x.dtype))
+    return tuple(outs)
 
 
 def _run(model, inputs, loss_fn, use_torch, monkeypatch):
@@ -40,7 +46,7 @@ def _run(model, inputs, loss_fn, use_torch, monkeypatch):
     for p in model.parameters():
         p.grad = None
     if use_torch:
-        monkeypatch.setattr(L, "sow_linear", _torch_sow_linear)
+        monkeypatch.setattr(L, "sow_linear_group", _torch_sow_linear_group)
     out = model(**inputs) if isinstance(inputs, dict) else model(inputs)
     logits = out.logits if hasattr(out, "logits") else out
     loss_fn(logits).backward()
@@ -76,11 +82,13 @@ def test_roberta_glue_shaped_keep_mode_fp32(monkeypatch):
     loss_fn = lambda logits: nn.functional.cross_entropy(logits.float(), labels)
     y_k, g_k = _run(model, {"input_ids": ids}, loss_fn, False, monkeypatch)
     y_t, g_t = _run(model, {"input_ids": ids}, loss_fn, True, monkeypatch)
-    assert _rel(y_k, y_t) < 1e-2
+    # fp32 modules run the fp32-faithful path (bf16x3 base products, fp32 outputs; the small rank-r factors and their
+    # gradients at bf16 input rounding with fp32 accumulation)
+    assert _rel(y_k, y_t) < 2e-3
     checked = 0
     for n in g_t:
         if "downscale_weights" in n or "upscale_weights" in n or "classifier" in n:
-            assert _rel(g_k[n], g_t[n]) < 2e-2, (n, _rel(g_k[n], g_t[n]))   # 2 layers of bf16 compute stacked
+            assert _rel(g_k[n], g_t[n]) < 1e-2, (n, _rel(g_k[n], g_t[n]))
             checked += 1
     assert checked >= 24
     # biases keep the reference's requires_grad state and receive a gradient when trainable
@@ -142,7 +150,7 @@ def test_llama7b_shaped_block_with_activation_checkpointing(monkeypatch):
     for n in g_plain:        # split-K partials are summed in a fixed order: bit-reproducible
         assert torch.equal(g_ckpt[n], g_plain[n]), n
     import sow_b200.layer as L
-    monkeypatch.setattr(L, "sow_linear", _torch_sow_linear)
+    monkeypatch.setattr(L, "sow_linear_group", _torch_sow_linear_group)
     gx_t, g_t = run(blk)
     monkeypatch.undo()
     assert _rel(gx_plain, gx_t) < 1e-2
