@@ -172,6 +172,7 @@ def run(args):
     groups.append({"params": special, "lr": args.sow_lr, "weight_decay": 0.0})
     opt = torch.optim.AdamW(groups)
     model.train()
+    fwd = torch.compile(model) if args.compile else model          # scripts/finetune.py:486-487
 
     gen = torch.Generator().manual_seed(1234)
     B, S = args.batch, args.seq
@@ -194,7 +195,7 @@ def run(args):
         b = batch()
         sync()
         t0 = time.perf_counter()
-        loss = model(**b).loss
+        loss = fwd(**b).loss
         loss.backward()
         if step in merge_at:                                        # simple_train.py:618-626 / run_glue.py:993-1002
             sync()
@@ -221,7 +222,7 @@ def run(args):
         "tokens_per_step": B * S, "sec_per_step": sec_total / max(len(times), 1),
         "tokens_per_s": B * S * len(times) / sec_total if sec_total > 0 else 0.0,
         "merge_sec": merge_s, "merges_in_timed_steps": timed_merge, "losses": losses, "init_method": init_method,
-        "sow_layers": len(sow),
+        "sow_layers": len(sow), "compiled": bool(args.compile),
     }
     print(json.dumps(out), flush=True)
 
@@ -243,6 +244,7 @@ def main():
     ap.add_argument("--init-method", default="normal_QR")
     ap.add_argument("--merge-at", type=int, nargs="*", default=[0],
                     help="0-based step indices (warm-up included) after whose backward the merge runs")
+    ap.add_argument("--compile", action="store_true", help="torch.compile(model) as scripts/finetune.py:486-487 does")
     ap.add_argument("--config1", action="store_true",
                     help="BASELINE.json configs[0]: llama_60m r=50, 16x256, 10 steps incl. one merge, fp32, CPU")
     args = ap.parse_args()

@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--act-ckpt", action="store_true", help="activation checkpointing (config 4: Llama-7B)")
     ap.add_argument("--param-dtype", default="bf16", choices=["bf16", "f32"],
                     help="dtype of the model parameters (the reference's GLUE scripts never set one: fp32)")
+    ap.add_argument("--compile", action="store_true",
+                    help="torch.compile(model) around the custom-op SoW layers (scripts/finetune.py:486-487); the reference-on-GPU "
+                         "baseline is compiled too.  Secondary row: the headline is the eager run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-optimizer", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
@@ -240,6 +243,7 @@ def main():
                           freeze_base=args.mode == "keep", activation_checkpointing=args.act_ckpt,
                           scale=1.0 if args.mode == "pretrain" else 0.125,
                           dtype=torch.float32 if args.param_dtype == "f32" else torch.bfloat16)
+    cfg.compile = bool(args.compile)
     trainer = SoWTrainer(cfg, device)
     B, S = args.batch, args.seq
     n_batches = 8
@@ -474,7 +478,7 @@ def main():
         torch.cuda.empty_cache()
         pd = "f32" if args.param_dtype == "f32" else "bf16"
         res = run_ref_subprocess(ref_workload_args(args) + ["--batch", B, "--steps", 5, "--warmup", 3, "--device", "cuda",
-                                                            "--dtype", pd, "--merge-at", 0])
+                                                            "--dtype", pd, "--merge-at", 0] + (["--compile"] if args.compile else []))
         kind = f"reference (unmodified package from baseline/_ref, eager torch ops, {pd}, torch.optim.AdamW) on the same B200"
         if res is None and not roberta:
             from oracle.cpu_trainer import time_cpu_training
@@ -496,6 +500,7 @@ def main():
                 "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "tokens_per_step": tokens_per_step,
                 "parallelism": f"dp{world}", "l2": "working set per step (>1 GB weights+activations) exceeds the 126 MB L2; no flush needed",
                 "optimizer": "FusedAdamW (sow_adam_multi)" if cfg.fused_optimizer else "torch.optim.AdamW",
+                "torch_compile": bool(args.compile),
             },
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8 + (B * 8 if roberta else 0),
                     "d2h_bytes_per_step": 4},

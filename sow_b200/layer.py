@@ -375,6 +375,14 @@ class SoWLinear(nn.Module):
             if self.bias is not None:
                 out = out + self.bias.to(out.dtype)
             return out
+        if torch.compiler.is_compiling():
+            # torch.compile(model) (scripts/finetune.py:486-487): registered custom ops, traced without a graph break
+            from .custom_ops import sow_linear_traceable
+            A_list, B_list = list(self.downscale_weights), list(self.upscale_weights)
+            A = A_list[0] if len(A_list) == 1 else torch.cat(A_list, dim=1)
+            B = B_list[0] if len(B_list) == 1 else torch.cat(B_list, dim=0)
+            W = self.acc_downweight if self.acc_downweight.numel() != 0 else None
+            return sow_linear_traceable(x, W, A, B, self.bias, self.scale)
         grp = self._group
         if grp is not None and grp.usable():
             return grp.forward(self, x)
@@ -448,6 +456,8 @@ def _merge_dense(mods: List[SoWLinear]) -> None:
             mod.acc_upweight = nn.Parameter(torch.empty(0, device=W_final.device), requires_grad=False)
         mod._w_shadow = None
         mod._w_shadow_key = None
+    from .custom_ops import invalidate_weight_cache
+    invalidate_weight_cache()
 
 
 def _merge_factored(mod: SoWLinear) -> None:

@@ -183,6 +183,8 @@ def load_sow(model: nn.Module, checkpoint_path: str) -> None:
     for m in sow_modules(model):                       # compute copies of W derived from the old values are stale now
         m._w_shadow = None
         m._w_shadow_key = None
+    from .custom_ops import invalidate_weight_cache
+    invalidate_weight_cache()
 
 
 def _device_of(model: nn.Module) -> torch.device:

@@ -107,6 +107,7 @@ class TrainConfig:
     freeze_base: bool = False            # fine-tuning: only the SoW factors train (run_glue.py:515-516,547-553)
     scale_after_first_merge: Optional[float] = None   # run_glue.py:996-1001 sets module.scale = 1/rank after the first merge
     dropout: float = 0.1                 # RoBERTa only (scripts/configs/roberta.json)
+    compile: bool = False                # torch.compile(model) as scripts/finetune.py:486-487 does (SoW layers = custom ops)
 
 
 class SoWTrainer:
@@ -165,6 +166,7 @@ class SoWTrainer:
         self.global_step = 0
         self.update_step = 0
         self.merges = 0
+        self.forward_fn = torch.compile(self.model) if cfg.compile else self.model
 
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None,
              attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -173,7 +175,7 @@ class SoWTrainer:
         if labels is None:
             labels = input_ids
         kw = {} if attention_mask is None else {"attention_mask": attention_mask}
-        loss = self.model(input_ids=input_ids, labels=labels, **kw).loss           # simple_train.py:611 / run_glue.py:978
+        loss = self.forward_fn(input_ids=input_ids, labels=labels, **kw).loss      # simple_train.py:611 / run_glue.py:978
         (loss / cfg.gradient_accumulation).backward()                              # :612-613 (+ overlapped all-reduce)
         accumulation_step = int(cfg.gradient_accumulation * cfg.sow_accumulation)
         G = cfg.gradient_accumulation

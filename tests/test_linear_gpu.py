@@ -163,8 +163,10 @@ def test_unsupported_feature_size_fails_loudly():
 
 
 def test_model_with_sow_layers_runs_under_torch_compile():
-    """scripts/finetune.py:486-487 wraps the model in torch.compile: the kernel call must stay opaque to dynamo (graph
-    break, eager execution of the C-ABI call) and give the same numbers as the uncompiled module."""
+    """scripts/finetune.py:486-487 wraps the model in torch.compile: the layers are registered torch.library custom ops
+    (sow_b200::linear_fwd / linear_bwd with fake implementations and an autograd formula), so dynamo traces through them
+    with ZERO graph breaks, and the compiled module gives the same numbers as the eager one."""
+    import torch._dynamo
     import torch.nn as nn
     from tn_gradient.prepare import SoWConfig, prepare_sow
     torch.manual_seed(0)
@@ -175,10 +177,39 @@ def test_model_with_sow_layers_runs_under_torch_compile():
     y0 = m(x)
     y0.float().pow(2).mean().backward()
     g0 = x.grad.clone()
+    gp0 = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
     x.grad = None
-    y1 = torch.compile(m)(x)
+    m.zero_grad()
+    torch._dynamo.reset()
+    ex = torch._dynamo.explain(m)(x)
+    assert ex.graph_break_count == 0, ex.break_reasons
+    assert ex.graph_count == 1
+    y1 = torch.compile(m, fullgraph=True)(x)
     y1.float().pow(2).mean().backward()
     assert torch.equal(y0, y1) and torch.equal(g0, x.grad)
+    for n, p in m.named_parameters():
+        if n in gp0:
+            assert torch.equal(gp0[n], p.grad), n
+
+
+def test_fp32_module_under_torch_compile_uses_the_fp32_path():
+    import torch._dynamo
+    import torch.nn as nn
+    from tn_gradient.prepare import SoWConfig, accumulate, prepare_sow
+    torch.manual_seed(0)
+    m = nn.Sequential(nn.Linear(256, 512), nn.Tanh(), nn.Linear(512, 256))
+    m = prepare_sow(m, SoWConfig(target_modules=["0", "2"], rank=8, device="cuda", init_method="normal", decompose="keep")).to("cuda")
+    x = torch.randn(64, 256, device="cuda")
+    torch._dynamo.reset()
+    cm = torch.compile(m, fullgraph=True)
+    with torch.no_grad():
+        y_e, y_c = m(x), cm(x)
+        assert y_c.dtype == torch.float32 and torch.equal(y_e, y_c)
+        for mod in (m[0], m[2]):
+            mod.upscale_weights[0].normal_(0, 0.05)
+        accumulate(m)                                  # in-place fp32 merge: the cached bf16 pieces of W must be dropped
+        y_e2, y_c2 = m(x), cm(x)
+        assert torch.equal(y_e2, y_c2) and not torch.equal(y_e, y_e2)
 
 
 def test_empty_batch_returns_empty_output_and_zero_grads():
