@@ -44,7 +44,11 @@ def parse_args():
     ap.add_argument("--compile", action="store_true",
                     help="torch.compile(model) around the custom-op SoW layers (scripts/finetune.py:486-487); the reference-on-GPU "
                          "baseline is compiled too.  Secondary row: the headline is the eager run")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay forward+backward+optimizer as ONE CUDA graph (single GPU; for small per-GPU batches, which are "
+                         "launch-bound).  Use --warmup >= 5: the capture happens on the 4th step after a merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-rows", action="store_true", help="skip the batch-16/64 and torch.compile rows")
     ap.add_argument("--no-fused-optimizer", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
     return ap.parse_args()
@@ -244,6 +248,7 @@ def main():
                           scale=1.0 if args.mode == "pretrain" else 0.125,
                           dtype=torch.float32 if args.param_dtype == "f32" else torch.bfloat16)
     cfg.compile = bool(args.compile)
+    cfg.cuda_graph = bool(args.cuda_graph)
     trainer = SoWTrainer(cfg, device)
     B, S = args.batch, args.seq
     n_batches = 8
@@ -319,6 +324,8 @@ def main():
     e2e_value = tokens_per_step * K / (float(ms2) / 1e3)
 
     # ---- instrumented pass: CUDA events around every kernel of each class (not part of `value`) -------------
+    trainer.cfg.cuda_graph = False           # the per-launch events need real launches, not a graph replay
+    trainer.invalidate_graph()
     ops.profile_enable(True)
     for i in range(args.profile_steps):
         _T.step(dev_batches[i % n_batches], i)
@@ -453,6 +460,46 @@ def main():
         replicas = {"consistent": True, "checked": "all parameters after the timed steps; merged W and re-initialised A of "
                     f"{len(mods)} SoW layers after one more merge (bit-exact across {world} ranks)"}
 
+    # ---- BASELINE.json config 2 sweeps the per-GPU batch {16, 64, 128}: small batches are launch-bound (~5 k launches per
+    # step), so they are reported eager AND replayed as one CUDA graph (rank 0, N=1 only; not part of `value`)
+    def quick_run(batch, graph=False, compiled=False, steps=12, warm=6):
+        import copy
+        c2 = copy.copy(cfg)
+        c2.batch_size, c2.cuda_graph, c2.compile = batch, graph, compiled
+        t2 = SoWTrainer(c2, device)
+        g2 = torch.Generator().manual_seed(99)
+        ids2 = [torch.randint(1, 32000, (batch, S), generator=g2, dtype=torch.int64).to(device) for _ in range(4)]
+        for i in range(warm):
+            t2.step(ids2[i % 4])
+            if i == 0:
+                t2.merge()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(steps):
+            l2 = t2.step(ids2[i % 4])
+        a1.record()
+        torch.cuda.synchronize()
+        ms2_ = a0.elapsed_time(a1) / steps
+        out = {"tokens_per_s": batch * S / (ms2_ / 1e3), "ms_per_step": ms2_, "loss": float(l2)}
+        del t2
+        torch.cuda.empty_cache()
+        return out
+
+    sweep, compiled_row = None, None
+    if rank == 0 and world == 1 and not roberta and not args.no_extra_rows and args.model == "llama_350m" and args.mode == "pretrain":
+        del trainer
+        trainer = None
+        torch.cuda.empty_cache()
+        sweep = {}
+        for b_ in (16, 64):
+            sweep[f"batch_{b_}"] = {"eager": quick_run(b_), "cuda_graph": quick_run(b_, graph=True)}
+        if not args.compile:
+            # torch.compile(model) as scripts/finetune.py:486-487: the SoW layers are registered custom ops (zero graph
+            # breaks), inductor fuses the stock HF element-wise code around them
+            compiled_row = quick_run(B, compiled=True, steps=8, warm=4)
+            compiled_row["what"] = "same step with torch.compile(model); SoW layers traced as sow_b200::linear_fwd/bwd custom ops"
+
     # ---- CPU baseline (rank 0, N=1 only): the reference's CPU path on the host cores -- the UNMODIFIED reference from
     # baseline/_ref when it is there (kind "reference"), else the oracle port ----
     cpu_baseline = None
@@ -474,7 +521,7 @@ def main():
     # bar of BASELINE.md section 5, reported beside the CPU baseline, not part of `value`
     gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del trainer
+        trainer = None
         torch.cuda.empty_cache()
         pd = "f32" if args.param_dtype == "f32" else "bf16"
         res = run_ref_subprocess(ref_workload_args(args) + ["--batch", B, "--steps", 5, "--warmup", 3, "--device", "cuda",
@@ -489,6 +536,12 @@ def main():
             gpu_eager = {"value": res["tokens_per_s"], "unit": "tokens/s", "kind": kind, "same_config": True,
                          "sample": f"5 steps of {B}x{S} tokens, {res['sec_per_step'] * 1e3:.1f} ms/step",
                          "speedup_of_this_build": value / res["tokens_per_s"]}
+        if compiled_row is not None:
+            resc = run_ref_subprocess(ref_workload_args(args) + ["--batch", B, "--steps", 5, "--warmup", 3, "--device", "cuda",
+                                                                 "--dtype", pd, "--merge-at", 0, "--compile"])
+            if resc is not None:
+                compiled_row["reference_compiled_tokens_per_s"] = resc["tokens_per_s"]
+                compiled_row["speedup_over_compiled_reference"] = compiled_row["tokens_per_s"] / resc["tokens_per_s"]
 
     if rank == 0:
         line = {
@@ -500,7 +553,7 @@ def main():
                 "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "tokens_per_step": tokens_per_step,
                 "parallelism": f"dp{world}", "l2": "working set per step (>1 GB weights+activations) exceeds the 126 MB L2; no flush needed",
                 "optimizer": "FusedAdamW (sow_adam_multi)" if cfg.fused_optimizer else "torch.optim.AdamW",
-                "torch_compile": bool(args.compile),
+                "torch_compile": bool(args.compile), "cuda_graph": bool(args.cuda_graph),
             },
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8 + (B * 8 if roberta else 0),
                     "d2h_bytes_per_step": 4},
@@ -510,6 +563,8 @@ def main():
             "cpu_baseline": cpu_baseline,
             "gpu_eager_baseline": gpu_eager,
             "replicas": replicas,
+            "batch_sweep": sweep,
+            "compiled": compiled_row,
             "clocks": clocks,
             "loss": final_loss,
         }

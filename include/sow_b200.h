@@ -255,6 +255,14 @@ int sow_adam_multi_ex(const void* chunks_dev, int n_chunks, int64_t total_elems,
                       double eps, double weight_decay, double bias_correction1, double bias_correction2, int decoupled,
                       int dtype, void* stream);
 
+/*
+ * CUDA-graph capturable variant: `step_dev` is a device fp32 counter that the call advances by one (a 1-thread kernel
+ * ahead of the update) and from which the update kernel derives both bias corrections, so a captured optimizer step
+ * replays correctly (torch.optim.AdamW(capturable=True) keeps state["step"] on the device for the same reason).
+ */
+int sow_adam_multi_dev(const void* chunks_dev, int n_chunks, int64_t total_elems, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, float* step_dev, int decoupled, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,7 @@ SIGNATURES = {
     "sow_adam_chunk_elems": (_i, []),
     "sow_adam_multi_ex": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _d, _d, _i, _i, _vp]),
     "sow_adam_multi": (_i, [_vp, _i, _d, _d, _d, _d, _d, _d, _d, _i, _i, _vp]),
+    "sow_adam_multi_dev": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _vp, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

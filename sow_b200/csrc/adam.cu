@@ -33,8 +33,25 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
   p -= h.step_size * (m / denom);
 }
 
+// CUDA-graph friendly step counter: the bias corrections are derived ON THE DEVICE from a counter that the launch
+// sequence itself advances, so a captured optimizer step replays with the right corrections (host-computed ones would
+// be frozen into the graph).
+__global__ void adam_step_inc_kernel(float* step) { *step += 1.0f; }
+
+__device__ __forceinline__ AdamHyper with_device_step(AdamHyper h, const float* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    const double t = static_cast<double>(*step_dev);
+    const double bc1 = 1.0 - pow(static_cast<double>(h.beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(h.beta2), t);
+    h.step_size = static_cast<float>(static_cast<double>(h.lr) / bc1);
+    h.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  }
+  return h;
+}
+
 __global__ void __launch_bounds__(256)
-adam_multi_bf16_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper h) {
+adam_multi_bf16_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper h0, const float* __restrict__ step_dev) {
+  const AdamHyper h = with_device_step(h0, step_dev);
   const AdamChunk c = chunks[blockIdx.x];
   __nv_bfloat16* p = static_cast<__nv_bfloat16*>(c.p);
   const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(c.g);
@@ -80,7 +97,8 @@ adam_multi_bf16_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper h) 
 }
 
 __global__ void __launch_bounds__(256)
-adam_multi_f32_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper h) {
+adam_multi_f32_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper h0, const float* __restrict__ step_dev) {
+  const AdamHyper h = with_device_step(h0, step_dev);
   const AdamChunk c = chunks[blockIdx.x];
   float* p = static_cast<float*>(c.p);
   const float* g = static_cast<const float*>(c.g);
@@ -128,14 +146,36 @@ int sow_adam_multi(const void* chunks_dev, int n_chunks, double lr, double beta1
                            bias_correction2, decoupled, dtype, stream_);
 }
 
+static int adam_launch(const void* chunks_dev, int n_chunks, int64_t total_elems, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, double bias_correction1, double bias_correction2, float* step_dev,
+                       int decoupled, int dtype, void* stream_);
+
 int sow_adam_multi_ex(const void* chunks_dev, int n_chunks, int64_t total_elems, double lr, double beta1, double beta2, double eps,
                       double weight_decay, double bias_correction1, double bias_correction2, int decoupled,
                       int dtype, void* stream_) {
+  SOWB_REQUIRE(bias_correction1 > 0.0 && bias_correction2 > 0.0, "sow_adam_multi: bias corrections must be positive");
+  return adam_launch(chunks_dev, n_chunks, total_elems, lr, beta1, beta2, eps, weight_decay, bias_correction1,
+                     bias_correction2, nullptr, decoupled, dtype, stream_);
+}
+
+int sow_adam_multi_dev(const void* chunks_dev, int n_chunks, int64_t total_elems, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, float* step_dev, int decoupled, int dtype, void* stream_) {
+  SOWB_REQUIRE(step_dev != nullptr, "sow_adam_multi_dev: null step counter");
+  return adam_launch(chunks_dev, n_chunks, total_elems, lr, beta1, beta2, eps, weight_decay, 1.0, 1.0, step_dev, decoupled,
+                     dtype, stream_);
+}
+
+static int adam_launch(const void* chunks_dev, int n_chunks, int64_t total_elems, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, double bias_correction1, double bias_correction2, float* step_dev,
+                       int decoupled, int dtype, void* stream_) {
   if (n_chunks <= 0) return SOWB_OK;
   SOWB_REQUIRE(chunks_dev != nullptr, "sow_adam_multi: null chunk table");
   if (int rc0 = ensure_context_for(chunks_dev)) return rc0;
-  SOWB_REQUIRE(bias_correction1 > 0.0 && bias_correction2 > 0.0, "sow_adam_multi: bias corrections must be positive");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (step_dev != nullptr) {
+    adam_step_inc_kernel<<<1, 1, 0, stream>>>(step_dev);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+  }
   AdamHyper h;
   h.lr = float(lr);
   h.beta1 = float(beta1);
@@ -151,9 +191,9 @@ int sow_adam_multi_ex(const void* chunks_dev, int n_chunks, int64_t total_elems,
   // algorithmic bytes: p, m, v read+written, g read = 7 accesses of the element size
   ProfileScope prof(stream, PROF_ADAM, 7.0 * double(total_elems) * (dtype == SOWB_BF16 ? 2 : 4));
   if (dtype == SOWB_BF16)
-    adam_multi_bf16_kernel<<<n_chunks, 256, 0, stream>>>(static_cast<const AdamChunk*>(chunks_dev), h);
+    adam_multi_bf16_kernel<<<n_chunks, 256, 0, stream>>>(static_cast<const AdamChunk*>(chunks_dev), h, step_dev);
   else if (dtype == SOWB_F32)
-    adam_multi_f32_kernel<<<n_chunks, 256, 0, stream>>>(static_cast<const AdamChunk*>(chunks_dev), h);
+    adam_multi_f32_kernel<<<n_chunks, 256, 0, stream>>>(static_cast<const AdamChunk*>(chunks_dev), h, step_dev);
   else
     return set_error(SOWB_EINVAL, "sow_adam_multi: unknown dtype %d", dtype);
   SOWB_CHECK_CUDA(cudaGetLastError());

@@ -469,6 +469,20 @@ def adam_multi(chunks: torch.Tensor, dtype: torch.dtype, lr, beta1, beta2, eps, 
     launch_counter["kernels"] += 1
 
 
+def adam_multi_dev(chunks: torch.Tensor, dtype: torch.dtype, lr, beta1, beta2, eps, weight_decay, step_dev: torch.Tensor,
+                   decoupled):
+    """Graph-capturable fused Adam: advances the device step counter and derives the bias corrections from it."""
+    lib = _lib.load()
+    if not (step_dev.is_cuda and step_dev.dtype == torch.float32 and step_dev.numel() == 1):
+        raise SowB200Error("adam_multi_dev: step must be a single-element fp32 CUDA tensor")
+    total = getattr(chunks, "_sow_total_elems", 0)
+    rc = lib.sow_adam_multi_dev(_p(chunks), chunks.shape[0], total, float(lr), float(beta1), float(beta2), float(eps),
+                                float(weight_decay), _p(step_dev), 1 if decoupled else 0, _dtype_code(dtype),
+                                _stream_ptr(chunks.device))
+    check(rc, "sow_adam_multi_dev")
+    launch_counter["kernels"] += 2
+
+
 # ---------------------------------------------------------------------------------------------------------
 # live profiling (bench.py)
 # ---------------------------------------------------------------------------------------------------------

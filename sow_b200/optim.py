@@ -190,15 +190,66 @@ class FusedAdamW(torch.optim.Optimizer):
     State layout is torch.optim.AdamW's (``state[p]["step"]`` tensor, ``exp_avg``, ``exp_avg_sq`` in the parameter
     dtype), so ``reset_optimizer`` (scripts/utils/training_utils.py:257-277), which REBINDS those tensors and zeroes
     ``step``, keeps working: pointers are re-resolved whenever a state tensor or gradient was rebound.
+
+    ``capturable=True`` (as in torch.optim.AdamW): ``state[p]["step"]`` lives on the device -- one fp32 counter shared by
+    the parameters of a group -- the kernels advance it and derive the bias corrections from it, and ``step()`` performs
+    no host-side arithmetic on it, so the whole optimizer step can be captured in a CUDA graph and replayed.
     """
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False,
-                 decoupled=True):
+                 decoupled=True, capturable=False):
         if amsgrad:
             raise SowB200Error("FusedAdamW: amsgrad is not implemented")
-        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, decoupled=decoupled)
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, decoupled=decoupled,
+                        capturable=capturable)
         super().__init__(params, defaults)
         self._tables = {}
+
+    def _step_capturable(self, gi, group):
+        """One device counter per (group, dtype); parameters whose ``step`` was rebound by reset_optimizer (a fresh zero
+        tensor) are folded back onto a shared counter restarted from that value."""
+        beta1, beta2 = group["betas"]
+        by_dtype = {}
+        for p in group["params"]:
+            if p.grad is None:
+                continue
+            if not p.is_cuda:
+                raise SowB200Error("FusedAdamW needs CUDA parameters (no CPU fallback)")
+            st = self.state[p]
+            if len(st) == 0 or "exp_avg" not in st:
+                st["step"] = None
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            g = p.grad if p.grad.dtype == p.dtype else p.grad.to(p.dtype)
+            by_dtype.setdefault(p.dtype, []).append((p, g, st))
+        for dtype, items in by_dtype.items():
+            ckey = ("counter", gi, dtype)
+            counter = self._tables.get(ckey)
+            steps = [st["step"] for _, _, st in items]
+            if counter is None or any(s is not counter for s in steps):
+                # (re)build the shared counter: happens outside graph capture (first step, or the step after a reset)
+                start = 0.0
+                for s_ in steps:
+                    if s_ is not None and s_ is not counter:
+                        start = float(s_)                       # rebound by reset_optimizer: restart from its value
+                        break
+                else:
+                    start = float(counter) if counter is not None else 0.0
+                counter = torch.full((1,), start, dtype=torch.float32, device=items[0][0].device)
+                self._tables[ckey] = counter
+                for _, _, st in items:
+                    st["step"] = counter
+            sig = tuple((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())
+                        for p, g, st in items)
+            key = (gi, dtype, len(items))
+            cached = self._tables.get(key)
+            if cached is None or cached[0] != sig:
+                cached = (sig, ops.build_adam_chunks([p.data for p, _, _ in items], [g for _, g, _ in items],
+                                                     [st["exp_avg"] for _, _, st in items],
+                                                     [st["exp_avg_sq"] for _, _, st in items]))
+                self._tables[key] = cached
+            ops.adam_multi_dev(cached[1], dtype, group["lr"], beta1, beta2, group["eps"], group["weight_decay"], counter,
+                               group["decoupled"])
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -207,6 +258,9 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for gi, group in enumerate(self.param_groups):
+            if group.get("capturable", False):
+                self._step_capturable(gi, group)
+                continue
             buckets = {}
             for p in group["params"]:
                 if p.grad is None:

@@ -108,6 +108,8 @@ class TrainConfig:
     scale_after_first_merge: Optional[float] = None   # run_glue.py:996-1001 sets module.scale = 1/rank after the first merge
     dropout: float = 0.1                 # RoBERTa only (scripts/configs/roberta.json)
     compile: bool = False                # torch.compile(model) as scripts/finetune.py:486-487 does (SoW layers = custom ops)
+    cuda_graph: bool = False             # capture forward + backward + optimizer step in one CUDA graph and replay it
+                                         # (small per-GPU batches are launch-bound: ~5 k launches per step); single GPU
 
 
 class SoWTrainer:
@@ -160,18 +162,79 @@ class SoWTrainer:
             groups.append({"params": self.trainable, "lr": cfg.lr, "weight_decay": cfg.weight_decay})
         self.sow_group_id = len(groups)
         groups.append({"params": self.special, "lr": cfg.sow_lr, "weight_decay": cfg.weight_decay})
-        self.optimizer = FusedAdamW(groups) if cfg.fused_optimizer else torch.optim.AdamW(groups)   # :502-506
+        if cfg.cuda_graph and not cfg.fused_optimizer:
+            raise ValueError("cuda_graph needs the fused optimizer (device-side step counter)")
+        self.optimizer = (FusedAdamW(groups, capturable=cfg.cuda_graph) if cfg.fused_optimizer
+                          else torch.optim.AdamW(groups))                                               # :502-506
         broadcast_parameters(model)                                                # DDP ctor semantics (:566-572)
         self.grad_sync = FlatGradSync(self.trainable + self.special, overlap=cfg.overlap_grad_sync, direct=self.special)
         self.global_step = 0
         self.update_step = 0
         self.merges = 0
         self.forward_fn = torch.compile(self.model) if cfg.compile else self.model
+        self._graph = None               # (CUDAGraph, static input_ids, static labels or None, static loss)
+        self._graph_warm = 0             # eager steps since the last (in)validation
+        self.graph_launches = 0
+        if cfg.cuda_graph and self.grad_sync.world > 1:
+            raise ValueError("cuda_graph is implemented for single-GPU steps (the bucket all-reduces are not captured)")
+
+    # ---- CUDA-graph replay of the whole micro-step ------------------------------------------------------------
+    def _graph_ok(self, attention_mask) -> bool:
+        cfg = self.cfg
+        if not cfg.cuda_graph or attention_mask is not None or cfg.gradient_accumulation != 1 or cfg.grad_clipping != 0.0:
+            return False
+        nxt = self.update_step                 # a merge fires inside step() when this is a multiple of sow_accumulation
+        return not (nxt > 0 and nxt % int(cfg.sow_accumulation) == 0)
+
+    def _graphed_step(self, input_ids, labels):
+        """Two eager steps after every (in)validation settle the addresses the graph will bake in (optimizer state, the
+        fused optimizer's pointer tables, workspaces, TMA descriptors); then one capture, then replays.  Gradient
+        buckets, in-place merges and the pointer-stable workspaces were laid out for exactly this."""
+        if self._graph is not None and (self._graph[1].shape != input_ids.shape or
+                                        (self._graph[2] is None) != (labels is None)):
+            self._graph = None
+            self._graph_warm = 0
+        if self._graph is None:
+            if self._graph_warm < 2:
+                self._graph_warm += 1
+                return None
+            static_ids = input_ids.clone()
+            static_lab = None if labels is None else labels.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            from . import ops
+            n0 = ops.launch_counter["kernels"]
+            with torch.cuda.graph(g):
+                loss = self._eager_body(static_ids, static_lab, None)
+            self.graph_launches = ops.launch_counter["kernels"] - n0      # sow_b200 kernels inside one replay
+            self._graph = (g, static_ids, static_lab, loss)
+        g, static_ids, static_lab, loss = self._graph
+        static_ids.copy_(input_ids, non_blocking=True)
+        if static_lab is not None:
+            static_lab.copy_(labels, non_blocking=True)
+        g.replay()
+        from . import ops
+        ops.launch_counter["kernels"] += self.graph_launches
+        self.global_step += 1
+        self.update_step += 1
+        return loss
+
+    def invalidate_graph(self) -> None:
+        self._graph = None
+        self._graph_warm = 0
 
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None,
              attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        cfg = self.cfg
+        if self._graph_ok(attention_mask):
+            out = self._graphed_step(input_ids, labels)
+            if out is not None:
+                return out
         self.global_step += 1
+        loss = self._eager_body(input_ids, labels, attention_mask)
+        return loss
+
+    def _eager_body(self, input_ids, labels, attention_mask):
+        cfg = self.cfg
         if labels is None:
             labels = input_ids
         kw = {} if attention_mask is None else {"attention_mask": attention_mask}
@@ -179,7 +242,8 @@ class SoWTrainer:
         (loss / cfg.gradient_accumulation).backward()                              # :612-613 (+ overlapped all-reduce)
         accumulation_step = int(cfg.gradient_accumulation * cfg.sow_accumulation)
         G = cfg.gradient_accumulation
-        if ((self.global_step % G or G == 1) and self.update_step > 0
+        capturing = torch.cuda.is_current_stream_capturing()
+        if (not capturing and (self.global_step % G or G == 1) and self.update_step > 0
                 and self.update_step % accumulation_step == 0):                    # :618-626
             self.merge()
         self.grad_sync.synchronize()          # DDP semantics: gradients are averaged on every micro-step (no no_sync)
@@ -189,13 +253,15 @@ class SoWTrainer:
             torch.nn.utils.clip_grad_norm_(self.trainable, cfg.grad_clipping)      # :631
         self.optimizer.step()                                                      # :646
         self.grad_sync.zero_grad()                                                 # :647 (one memset per bucket)
-        self.update_step += 1
+        if not capturing:
+            self.update_step += 1
         return loss.detach()
 
     def merge(self) -> None:
         accumulate(self.model)
         reset_optimizer(self.optimizer, group_id=self.sow_group_id)
         self.merges += 1
+        self.invalidate_graph()                # W / optimizer-state addresses may have changed
         if self.merges == 1 and self.cfg.scale_after_first_merge is not None:      # run_glue.py:996-1001
             for m in sow_modules(self.model):
                 m.scale = self.cfg.scale_after_first_merge
