@@ -447,8 +447,24 @@ def main():
 
     # ---- multi-GPU correctness (world > 1): replicas must hold identical parameters after the timed steps, and identical
     # merged W / re-initialised A after one more merge (raises on a mismatch)
-    replicas = None
+    replicas, comm = None, None
     if world > 1:
+        # how much of the gradient all-reduce is NOT hidden behind backward: CUDA events on the compute stream around the
+        # wait for the bucket all-reduces, 5 steps
+        trainer.comm_events = []
+        for i in range(5):
+            _T.step(dev_batches[i % n_batches], i)
+        torch.cuda.synchronize()
+        waits = [a.elapsed_time(b) for a, b in trainer.comm_events]
+        trainer.comm_events = None
+        w_ms = torch.tensor([statistics.median(waits)], device=device, dtype=torch.float64)
+        dist.all_reduce(w_ms, op=dist.ReduceOp.MAX)
+        comm = {"exposed_allreduce_wait_ms": float(w_ms), "of_step_ms": step_ms,
+                "buckets_bytes": [int(b["flat"].numel() * b["flat"].element_size()) for b in trainer.grad_sync.buckets],
+                "note": "max over ranks of the median device-side wait between the end of backward and the completion of the last "
+                        "bucket all-reduce (NCCL AVG, one call per flat bucket, launched from post-accumulate-grad hooks as the "
+                        "bucket fills); the last bucket holds embed_tokens, whose gradient is produced by the very last backward "
+                        "kernel, so its all-reduce cannot overlap anything"}
         from sow_b200.parallel import assert_replicas_consistent
         from sow_b200.surgery import sow_modules
         assert_replicas_consistent(list(trainer.model.parameters()), "parameter after the timed steps")
@@ -563,6 +579,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "gpu_eager_baseline": gpu_eager,
             "replicas": replicas,
+            "comm": comm,
             "batch_sweep": sweep,
             "compiled": compiled_row,
             "clocks": clocks,

@@ -175,6 +175,7 @@ class SoWTrainer:
         self._graph = None               # (CUDAGraph, static input_ids, static labels or None, static loss)
         self._graph_warm = 0             # eager steps since the last (in)validation
         self.graph_launches = 0
+        self.comm_events = None          # list of (event, event) pairs when the exposed all-reduce time is being measured
         if cfg.cuda_graph and self.grad_sync.world > 1:
             raise ValueError("cuda_graph is implemented for single-GPU steps (the bucket all-reduces are not captured)")
 
@@ -246,7 +247,16 @@ class SoWTrainer:
         if (not capturing and (self.global_step % G or G == 1) and self.update_step > 0
                 and self.update_step % accumulation_step == 0):                    # :618-626
             self.merge()
-        self.grad_sync.synchronize()          # DDP semantics: gradients are averaged on every micro-step (no no_sync)
+        if self.comm_events is not None and not capturing:
+            # device-side measurement of the EXPOSED part of the gradient all-reduce: the compute stream reaches e0 when
+            # backward is done and e1 when every bucket's all-reduce has finished (bench.py, world > 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.grad_sync.synchronize()
+            e1.record()
+            self.comm_events.append((e0, e1))
+        else:
+            self.grad_sync.synchronize()      # DDP semantics: gradients are averaged on every micro-step (no no_sync)
         if self.global_step % G != 0:                                              # :628
             return loss.detach()
         if cfg.grad_clipping != 0.0:
