@@ -158,11 +158,11 @@ struct Segment {
 
 // Operand A of D = A.B: logical [M, K].  K-major  <=> stored [M rows, K cols];  MN-major <=> stored [K rows, M cols].
 // Operand B of D = A.B: logical [K, N].  K-major  <=> stored [N rows, K cols];  MN-major <=> stored [K rows, N cols].
-template <int BN, bool A_MN, bool B_MN, int EPI, int MT = 1>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32, int ldc, int M, int N,
                        const float* alpha_blocks, int n_alpha, const void* bias, bool split_k, cudaStream_t stream,
                        int prof_class, double alg_flops, int* splits_out = nullptr) {
-  using S = GemmSmem<BN, MT>;
+  using S = GemmSmem<BN>;
   if (nseg < 1 || nseg > kMaxSeg) return set_error(SOWB_EINVAL, "launch_gemm: %d segments (max %d)", nseg, kMaxSeg);
   GemmMaps maps;
   GemmParams p;
@@ -188,7 +188,7 @@ static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32
   p.M = M;
   p.N = N;
   p.nseg = nseg;
-  p.m_tiles = ceil_div(M, kBM * MT);      // work rows: MT tiles of 128 rows each
+  p.m_tiles = ceil_div(M, kBM);
   p.n_tiles = ceil_div(N, BN);
   const int kb_total = kb;
   const int sms = num_sms();
@@ -210,7 +210,7 @@ static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32
   if (splits_out) *splits_out = p.splits;
   const int total = p.m_tiles * p.n_tiles * p.splits;
   if (total <= 0 || kb_total <= 0) return SOWB_OK;
-  auto kern = sow_gemm_kernel<BN, A_MN, B_MN, EPI, MT>;
+  auto kern = sow_gemm_kernel<BN, A_MN, B_MN, EPI>;
   SOWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   const int grid = total < sms ? total : sms;
   ProfileScope prof(stream, prof_class, alg_flops);   // algorithmic flops: un-padded ranks
@@ -234,19 +234,19 @@ constexpr int kBiasParts = 64;
 // tile width of the skinny GEMMs over the concatenated rank dimension R (a multiple of 64)
 static int skinny_bn(int R) { return R >= 256 ? 256 : R; }
 
-template <bool A_MN, bool B_MN, int EPI, int MT = 1>
+template <bool A_MN, bool B_MN, int EPI>
 static int launch_skinny(int R, const Segment* seg, int nseg, void* C_bf16, float* C_f32, int ldc, int M,
                          const float* alpha, int n_alpha, bool split_k, cudaStream_t stream, int prof_class,
                          double alg_flops, int* splits_out = nullptr) {
   switch (skinny_bn(R)) {
     case 64:
-      return launch_gemm<64, A_MN, B_MN, EPI, MT>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
+      return launch_gemm<64, A_MN, B_MN, EPI>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
     case 128:
-      return launch_gemm<128, A_MN, B_MN, EPI, MT>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
+      return launch_gemm<128, A_MN, B_MN, EPI>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
     case 192:
-      return launch_gemm<192, A_MN, B_MN, EPI, MT>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
+      return launch_gemm<192, A_MN, B_MN, EPI>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
     default:
-      return launch_gemm<256, A_MN, B_MN, EPI, MT>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
+      return launch_gemm<256, A_MN, B_MN, EPI>(seg, nseg, C_bf16, C_f32, ldc, M, R, alpha, n_alpha, nullptr, split_k, stream, prof_class, alg_flops, splits_out);
   }
 }
 
@@ -440,16 +440,8 @@ int sow_group_fwd(const void* x, const void* x_lo, const sowb_group_member* m, i
                       Operand{A_cat, uint64_t(in), uint64_t(R), uint64_t(R)}, in}};
     int rsum = 0;
     for (int i = 0; i < n; ++i) rsum += m[i].r;
-    // two M tiles per CTA share each factor tile (more streamed bytes of x in flight per SM, see GemmSmem) once T is
-    // large enough to keep >= 80 % of the SMs busy with pairs
-    if (T * 10 >= int64_t(2) * kBM * num_sms() * 8)
-      rc = launch_skinny<false, true, EPI_BF16_TMA, 2>(R, sg, f32 ? 2 : 1, t_cat, nullptr, R, static_cast<int>(T), alpha, nb,
-                                                       false, stream, PROF_GEMM_SKINNY,
-                                                       2.0 * double(T) * double(in) * double(rsum));
-    else
-      rc = launch_skinny<false, true, EPI_BF16_TMA>(R, sg, f32 ? 2 : 1, t_cat, nullptr, R, static_cast<int>(T), alpha, nb,
-                                                    false, stream, PROF_GEMM_SKINNY,
-                                                    2.0 * double(T) * double(in) * double(rsum));
+    rc = launch_skinny<false, true, EPI_BF16_TMA>(R, sg, f32 ? 2 : 1, t_cat, nullptr, R, static_cast<int>(T), alpha, nb, false,
+                                                  stream, PROF_GEMM_SKINNY, 2.0 * double(T) * double(in) * double(rsum));
     if (rc) return rc;
   }
   // y_i = x . W_i + t_i . B_i (+ bias_i)
