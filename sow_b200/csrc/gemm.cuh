@@ -65,13 +65,19 @@ struct GemmParams {
   int ldc;
 };
 
-template <int BN>
+// MT = M tiles (of 128 rows) per CTA.  MT = 2 makes the CTA tile 256 x BN: both M tiles are multiplied by the SAME B tile,
+// so a k-block moves 32 KB (A) + 32 KB (B) from L2 for twice the MACs of the 128 x 256 tile (16 + 32 KB) -- 62 instead of 94
+// B/clk/SM at full tensor rate, which is what holds the 17-k-block forward tiles at ~65 % tensor-pipe activity.  The two
+// accumulators take the place of the two TMEM stages, so the epilogue of a work item is not overlapped with the next one's
+// MMAs; the launcher picks MT = 2 only where the wave quantisation of the larger tiles does not eat the gain.
+template <int BN, int MT = 1>
 struct GemmSmem {
-  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kABytes = MT * kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // leave room for 2 staging buffers (32 KB) + barriers inside the 227 KB opt-in limit
-  static constexpr int kStages = (BN >= 192) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kFit = (232448 - 1024 - 2 * kStageCBytes - 256) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kStagingBytes = 2 * kStageCBytes;
   static constexpr int kBarBytes = 256;
@@ -79,10 +85,11 @@ struct GemmSmem {
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int MT = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, MT>;
+  static_assert(MT == 1 || MT == 2, "one or two M tiles per CTA");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -135,7 +142,7 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int split = w % p.splits;
       const int tile = w / p.splits;
-      const int m0 = (tile / p.n_tiles) * kBM;
+      const int m0 = (tile / p.n_tiles) * kBM * MT;
       const int n0 = (tile % p.n_tiles) * BN;
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
@@ -150,13 +157,17 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const CUtensorMap* ma = &maps.a[seg];
         const CUtensorMap* mb = &maps.b[seg];
         const int k0 = (kb - (seg ? p.kb_end[seg - 1] : 0)) * kBK;
-        if (A_MN) {
-          // global [K rows, M contiguous]: two boxes of (64 M) x (64 K)
 #pragma unroll
-          for (int j = 0; j < kBM / 64; ++j) tma_load_2d(sa + j * 8192, ma, &full_bar[stage], m0 + 64 * j, k0);
-        } else {
-          // global [M rows, K contiguous]: one box of (64 K) x (128 M)
-          tma_load_2d(sa, ma, &full_bar[stage], k0, m0);
+        for (int mt = 0; mt < MT; ++mt) {
+          if (A_MN) {
+            // global [K rows, M contiguous]: two boxes of (64 M) x (64 K) per M tile
+#pragma unroll
+            for (int j = 0; j < kBM / 64; ++j)
+              tma_load_2d(sa + mt * 16384 + j * 8192, ma, &full_bar[stage], m0 + mt * kBM + 64 * j, k0);
+          } else {
+            // global [M rows, K contiguous]: one box of (64 K) x (128 M) per M tile (rows beyond M are zero-filled)
+            tma_load_2d(sa + mt * 16384, ma, &full_bar[stage], k0, m0 + mt * kBM);
+          }
         }
         if (B_MN) {
           // global [K rows, N contiguous]: BN/64 boxes of (64 N) x (64 K)
@@ -190,7 +201,7 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BN;
+      const uint32_t tmem_d = tmem_base + (MT == 2 ? 0 : acc * BN);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -201,6 +212,10 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
           const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
           umma_bf16(tmem_d, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          if (MT == 2) {
+            const uint64_t ad1 = make_smem_desc(sa + 16384 + k * a_kstep, a_lbo, a_sbo);
+            umma_bf16(tmem_d + BN, ad1, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == S::kStages) {
@@ -209,7 +224,7 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
       }
       umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-      if (++acc == 2) {
+      if (++acc == (MT == 2 ? 1 : 2)) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -224,11 +239,15 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     uint32_t boxes_issued = 0;  // TMA-store boxes issued so far by this CTA (for staging double-buffer)
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tile = w / p.splits;
-      const int m0 = (tile / p.n_tiles) * kBM;
+      const int m0_first = (tile / p.n_tiles) * kBM * MT;
       const int n0 = (tile % p.n_tiles) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int m0 = m0_first + mt * kBM;
+      if (m0 >= p.M) break;  // uniform across the CTA
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (MT == 2 ? mt * BN : acc * BN);
       if (EPI == EPI_BF16_TMA) {
 #pragma unroll 1
         for (int b = 0; b < BN / kStoreBoxCols; ++b) {
@@ -336,10 +355,11 @@ sow_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
         }
       }
+      }  // mt
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) {
+      if (++acc == (MT == 2 ? 1 : 2)) {
         acc = 0;
         acc_phase ^= 1;
       }

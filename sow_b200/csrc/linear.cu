@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 
 namespace sowb {
 
@@ -158,11 +159,11 @@ struct Segment {
 
 // Operand A of D = A.B: logical [M, K].  K-major  <=> stored [M rows, K cols];  MN-major <=> stored [K rows, M cols].
 // Operand B of D = A.B: logical [K, N].  K-major  <=> stored [N rows, K cols];  MN-major <=> stored [K rows, N cols].
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int MT = 1>
 static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32, int ldc, int M, int N,
                        const float* alpha_blocks, int n_alpha, const void* bias, bool split_k, cudaStream_t stream,
                        int prof_class, double alg_flops, int* splits_out = nullptr) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, MT>;
   if (nseg < 1 || nseg > kMaxSeg) return set_error(SOWB_EINVAL, "launch_gemm: %d segments (max %d)", nseg, kMaxSeg);
   GemmMaps maps;
   GemmParams p;
@@ -188,7 +189,7 @@ static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32
   p.M = M;
   p.N = N;
   p.nseg = nseg;
-  p.m_tiles = ceil_div(M, kBM);
+  p.m_tiles = ceil_div(M, kBM * MT);      // work rows: MT tiles of 128 rows each
   p.n_tiles = ceil_div(N, BN);
   const int kb_total = kb;
   const int sms = num_sms();
@@ -210,7 +211,7 @@ static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32
   if (splits_out) *splits_out = p.splits;
   const int total = p.m_tiles * p.n_tiles * p.splits;
   if (total <= 0 || kb_total <= 0) return SOWB_OK;
-  auto kern = sow_gemm_kernel<BN, A_MN, B_MN, EPI>;
+  auto kern = sow_gemm_kernel<BN, A_MN, B_MN, EPI, MT>;
   SOWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   const int grid = total < sms ? total : sms;
   ProfileScope prof(stream, prof_class, alg_flops);   // algorithmic flops: un-padded ranks
@@ -220,6 +221,24 @@ static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// 256 x 256 CTA tiles (MT = 2) cut the L2 -> SM operand traffic per MAC by a third, but they halve the number of work items
+// (wave quantisation) and expose the epilogue (no second TMEM stage).  Measured at T = 32768 / 8192 (tools/bench_group.py,
+// SOWB_BIG_TILES=0/1): Llama-7B gate/up forward 590 -> 514 us (1441 TFLOP/s) and its dX 1006 -> 980 us; Llama-350M gate/up
+// forward 155.5 -> 151.9 us; but q/k/v forward 60.7 -> 67.6 us (512 items = 3.46 waves) and down dX 140.6 -> 152.7 us
+// (17 k-blocks: the exposed epilogue costs more than the traffic saves).  Hence: only when the last wave is >= 93 % full
+// AND the K loop is long enough (>= 32 k-blocks) to amortise the epilogue.
+static bool use_big_tiles(int M, int N, int kb_total) {
+  static const int knob = []() {
+    const char* e = getenv("SOWB_BIG_TILES");   // tuning knob: 0 never, 1 always, unset = by wave efficiency
+    return e ? atoi(e) : -1;
+  }();
+  if (knob >= 0) return knob != 0;
+  const int items = ceil_div(M, 2 * kBM) * ceil_div(N, 256);
+  const int sms = num_sms();
+  const int waves = ceil_div(items, sms);
+  return kb_total >= 32 && items >= 2 * sms && double(items) / (double(waves) * sms) >= 0.93;
+}
 
 // number of split-K partials launch_gemm<BN, ..., EPI_F32_PARTIAL> produces for an [M x N] output contracted over K
 static int splitk_count(int M, int N, int BN, int K) {
@@ -471,6 +490,9 @@ int sow_group_fwd(const void* x, const void* x_lo, const sowb_group_member* m, i
       rc = launch_gemm<256, false, true, EPI_F32_TMA>(segs, ns, nullptr, static_cast<float*>(m[i].y), m[i].out,
                                                       static_cast<int>(T), m[i].out, &one, 1, m[i].bias, false, stream,
                                                       PROF_GEMM_FWD, fl);
+    else if (use_big_tiles(static_cast<int>(T), m[i].out, ceil_div(in, kBK) * (m[i].W != nullptr) + L.rpad[i] / kBK))
+      rc = launch_gemm<256, false, true, EPI_BF16_TMA, 2>(segs, ns, m[i].y, nullptr, m[i].out, static_cast<int>(T), m[i].out,
+                                                          &one, 1, m[i].bias, false, stream, PROF_GEMM_FWD, fl);
     else
       rc = launch_gemm<256, false, true, EPI_BF16_TMA>(segs, ns, m[i].y, nullptr, m[i].out, static_cast<int>(T), m[i].out,
                                                        &one, 1, m[i].bias, false, stream, PROF_GEMM_FWD, fl);
@@ -694,6 +716,9 @@ int sow_group_bwd(const void* x, const void* A_cat, const void* t_cat, const sow
     if (f32)
       rc = launch_gemm<256, false, false, EPI_F32_TMA>(segs, ns, nullptr, static_cast<float*>(dx), in, Ti, in, &one, 1, nullptr,
                                                        false, stream, PROF_GEMM_DX, 2.0 * double(T) * double(in) * kalg);
+    else if (use_big_tiles(Ti, in, static_cast<int>(kalg) / kBK))
+      rc = launch_gemm<256, false, false, EPI_BF16_TMA, 2>(segs, ns, dx, nullptr, in, Ti, in, &one, 1, nullptr, false, stream,
+                                                           PROF_GEMM_DX, 2.0 * double(T) * double(in) * kalg);
     else
       rc = launch_gemm<256, false, false, EPI_BF16_TMA>(segs, ns, dx, nullptr, in, Ti, in, &one, 1, nullptr, false, stream,
                                                         PROF_GEMM_DX, 2.0 * double(T) * double(in) * kalg);
