@@ -214,6 +214,10 @@ class SharedInputGroup:
         self.misses = 0
         self.enabled = True
 
+    def usable_traced(self) -> bool:
+        ms = self.members
+        return self.enabled and 2 <= len(ms) <= 4 and all(m.n_iter == 1 and m.acc_upweight.numel() == 0 for m in ms)
+
     def usable(self) -> bool:
         ms = self.members
         if not self.enabled or len(ms) < 2 or len(ms) > 4:
@@ -226,6 +230,23 @@ class SharedInputGroup:
                 return False
             n_dense += m.acc_downweight.numel() != 0
         return n_dense <= 3
+
+    def forward_traced(self, idx: int, x: torch.Tensor) -> torch.Tensor:
+        """Same protocol while dynamo traces (torch.compile): tensor identity is the identity of the traced value, the
+        whole group is ONE sow_b200::group_fwd node in the graph."""
+        c = self.cache
+        if c is not None and c[0] is x and idx in c[3]:
+            y = c[3].pop(idx)
+            if not c[3]:
+                self.cache = None
+            return y
+        from .custom_ops import sow_group_traceable
+        ms = self.members
+        Ws = [m.acc_downweight if m.acc_downweight.numel() != 0 else None for m in ms]
+        ys = sow_group_traceable(x, Ws, [m.downscale_weights[0] for m in ms], [m.upscale_weights[0] for m in ms],
+                                 [m.bias for m in ms], [m.scale for m in ms])
+        self.cache = (x, 0, True, {i: y for i, y in enumerate(ys) if i != idx})
+        return ys[idx]
 
     def forward(self, mod: "SoWLinear", x: torch.Tensor) -> torch.Tensor:
         idx = self.index[id(mod)]
@@ -320,6 +341,7 @@ class SoWLinear(nn.Module):
         self._w_shadow = None       # bf16 compute copy of a non-bf16 acc_downweight
         self._w_shadow_key = None
         self._group = None          # SharedInputGroup of the projections that read the same input (surgery.group_shared_inputs)
+        self._group_index = -1
         if init_params:
             self.reset_parameters()
 
@@ -377,6 +399,9 @@ class SoWLinear(nn.Module):
             return out
         if torch.compiler.is_compiling():
             # torch.compile(model) (scripts/finetune.py:486-487): registered custom ops, traced without a graph break
+            grp = self._group
+            if grp is not None and self._group_index >= 0 and self.n_iter == 1 and grp.usable_traced():
+                return grp.forward_traced(self._group_index, x)
             from .custom_ops import sow_linear_traceable
             A_list, B_list = list(self.downscale_weights), list(self.upscale_weights)
             A = A_list[0] if len(A_list) == 1 else torch.cat(A_list, dim=1)

@@ -130,8 +130,9 @@ def group_shared_inputs(model: nn.Module, name_sets=SHARED_INPUT_SETS) -> int:
             if len(members) < 2 or len({m.in_features for m in members}) != 1:
                 continue
             grp = SharedInputGroup(members)
-            for m in members:
+            for i, m in enumerate(members):
                 m._group = grp
+                m._group_index = i
             formed += 1
     return formed
 

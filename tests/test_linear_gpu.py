@@ -427,3 +427,33 @@ def test_factor_gradients_land_in_the_flat_bucket_without_a_copy():
             assert float((p.grad.float() - 2 * q.grad.float()).norm() / (2 * q.grad.float().norm() + 1e-20)) < 1e-2, n
     sync.zero_grad()
     assert all(p.grad is None for p in factors) and float(flat.abs().max()) == 0.0
+
+
+def test_shared_input_groups_stay_grouped_under_torch_compile():
+    """Compiled models keep the q/k/v and gate/up groups: dynamo traces the sibling calls into ONE sow_b200::group_fwd node
+    per group (zero graph breaks), and the result matches the eager grouped execution."""
+    import torch._dynamo
+    h, ff, r = 256, 512, 8
+    blk = _mk_block(h, ff, r, True)
+    x = torch.randn(2, 96, h, device="cuda", dtype=torch.bfloat16)
+    xe = x.clone().requires_grad_(True)
+    ye = blk(xe)
+    ye.float().pow(2).mean().backward()
+    ge = {n: p.grad.clone() for n, p in blk.named_parameters() if p.grad is not None}
+    gxe = xe.grad.clone()
+    blk.zero_grad()
+    torch._dynamo.reset()
+    ex = torch._dynamo.explain(blk)(x)
+    assert ex.graph_break_count == 0, ex.break_reasons
+    targets = [str(n.target) for g in ex.graphs for n in g.graph.nodes if n.op == "call_function"]
+    assert sum("group_fwd" in t for t in targets) == 2 and sum("linear_fwd" in t for t in targets) == 1, targets
+    assert blk.q_proj._group.cache is None and blk.gate_proj._group.cache is None
+    xc = x.clone().requires_grad_(True)
+    yc = torch.compile(blk, fullgraph=True)(xc)
+    yc.float().pow(2).mean().backward()
+    # inductor fuses the element-wise glue (silu * up, q + cat(k, v)) in fp32: same function, different bf16 rounding points
+    assert float((ye.float() - yc.float()).norm() / ye.float().norm()) < 1e-2
+    assert float((gxe.float() - xc.grad.float()).norm() / gxe.float().norm()) < 1e-2
+    for n, p in blk.named_parameters():
+        if n in ge:
+            assert float((ge[n].float() - p.grad.float()).norm() / (ge[n].float().norm() + 1e-20)) < 1e-2, n
