@@ -34,6 +34,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -623,6 +624,42 @@ sow_merge_f32_kernel(const MergeF32Entry* __restrict__ tab, int n_entries, int t
 
 using namespace sowb;
 
+// Host -> device upload of a descriptor table without blocking the host: the table is copied into one of a few cached
+// PINNED staging buffers and sent with a truly asynchronous cudaMemcpyAsync (a pageable source of more than 64 KB makes
+// the "async" copy synchronise the calling thread with the stream, and is illegal during stream capture).  A slot is
+// reused only after the copy that last read it has completed (event per slot).
+namespace {
+struct PinnedRing {
+  static constexpr int kSlots = 4;
+  void* buf[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kSlots] = {0, 0, 0, 0};
+  cudaEvent_t ev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  int next = 0;
+  std::mutex mu;
+};
+PinnedRing g_ring;
+
+int upload_table(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_ring.mu);
+  const int s = g_ring.next;
+  g_ring.next = (g_ring.next + 1) % PinnedRing::kSlots;
+  if (g_ring.ev[s] == nullptr) SOWB_CHECK_CUDA(cudaEventCreateWithFlags(&g_ring.ev[s], cudaEventDisableTiming));
+  else SOWB_CHECK_CUDA(cudaEventSynchronize(g_ring.ev[s]));
+  if (g_ring.cap[s] < bytes) {
+    if (g_ring.buf[s] != nullptr) SOWB_CHECK_CUDA(cudaFreeHost(g_ring.buf[s]));
+    g_ring.buf[s] = nullptr;
+    g_ring.cap[s] = 0;
+    const size_t want = std::max(bytes, size_t(256) << 10);
+    SOWB_CHECK_CUDA(cudaHostAlloc(&g_ring.buf[s], want, cudaHostAllocDefault));
+    g_ring.cap[s] = want;
+  }
+  memcpy(g_ring.buf[s], src_host, bytes);
+  SOWB_CHECK_CUDA(cudaMemcpyAsync(dst_dev, g_ring.buf[s], bytes, cudaMemcpyHostToDevice, stream));
+  SOWB_CHECK_CUDA(cudaEventRecord(g_ring.ev[s], stream));
+  return SOWB_OK;
+}
+}  // namespace
+
 static long long* g_merge_ts = nullptr;   // debug timeline buffer (device), see sow_merge_debug_timeline
 
 extern "C" {
@@ -664,7 +701,7 @@ static int merge_grouped_f32(const sowb_merge_entry* entries, int n, void* table
     tiles += ceil_div(e.in, kMfBM) * d.n_tiles;
     bytes += 4.0 * e.in * e.out * (1 + (e.W_prev != nullptr)) + 4.0 * e.r * (double(e.in) + e.out);
   }
-  SOWB_CHECK_CUDA(cudaMemcpyAsync(table_dev, host.data(), size_t(n) * sizeof(MergeF32Entry), cudaMemcpyHostToDevice, stream));
+  if (int rcu = upload_table(table_dev, host.data(), size_t(n) * sizeof(MergeF32Entry), stream)) return rcu;
   const int grid = std::min(tiles, num_sms() * 8);
   ProfileScope prof(stream, PROF_MERGE, bytes);
   sow_merge_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const MergeF32Entry*>(table_dev), n, tiles);
@@ -750,8 +787,8 @@ int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* t
         bytes += 2.0 * d.in * d.out * (1 + d.has_prev) + 2.0 * d.r * (double(d.in) + d.out);
       }
       // stream-ordered: an earlier launch on this stream that still reads the table finishes before this copy
-      SOWB_CHECK_CUDA(cudaMemcpyAsync(table_dev, host.data() + first, cnt * sizeof(MergeDevEntry),
-                                      cudaMemcpyHostToDevice, stream));
+      rc = upload_table(table_dev, host.data() + first, cnt * sizeof(MergeDevEntry), stream);
+      if (rc) return rc;
       const int grid = tiles < sms ? tiles : sms;
       ProfileScope prof(stream, PROF_MERGE, bytes);
       static const int prefetch = []() {

@@ -149,13 +149,21 @@ thin_qr_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __rest
 //     G = X^T X (fp64, all SMs)  ->  G = L L^T (one CTA)  ->  q_row . L^T = x_row by forward substitution (all SMs)
 // R = L^T has a positive diagonal: same sign convention as the CGS2 kernel.  A column whose pivot vanishes
 // (d_j <= 1e-12 * G_jj: linearly dependent on the previous ones) yields a ZERO column of Q, like CGS2's zero-norm rule.
+// Orthogonality degrades as cond(X)^2 * 2^-53 = 2^-53 / min_j(d_j / G_jj): when a surviving pivot ratio drops below
+// 1e-8 (cond >~ 1e4 -- e.g. the all-positive, nearly rank-one leading columns of a TT-Adam second-moment unfolding) the
+// Cholesky kernel raises the matrix's flag and a SECOND Cholesky-QR pass over Q (CholeskyQR2, same three kernels, still
+// fp64 inside) restores |Q^T Q - I| to rounding level without moving the subspace (a re-orthogonalised fp32 Gram-Schmidt
+// would keep Q orthonormal but tilt its span by eps32 * cond).  For well-conditioned inputs the three extra launches exit
+// at their first instruction.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCqMaxR = 64;
 constexpr int kCqRows = 128;
 constexpr size_t kCqWsPerBatch = (kCqMaxR * kCqMaxR + kCqMaxR) * sizeof(double);
 
 __global__ void __launch_bounds__(256)
-cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __restrict__ ws, int m, int r) {
+cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __restrict__ ws, int m, int r,
+               const int* __restrict__ only_if) {
+  if (only_if != nullptr && only_if[blockIdx.y] == 0) return;      // second pass: flagged matrices only
   __shared__ float sx[kCqRows][kCqMaxR + 1];
   const float* Xb = X + blockIdx.y * x_bs;
   double* G = ws + blockIdx.y * (kCqMaxR * kCqMaxR + kCqMaxR);
@@ -197,7 +205,8 @@ cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __res
 // Right-looking Cholesky with the column scaling deferred: step j only needs the pivot d_j = A[j][j] and the unscaled
 // column j, A[i][k] -= A[i][j] A[k][j] / d_j, so there is ONE barrier per step; L = A . diag(d)^-1/2 at the end.
 __global__ void __launch_bounds__(1024)
-cq_chol_kernel(double* __restrict__ ws, int r) {
+cq_chol_kernel(double* __restrict__ ws, int r, int* __restrict__ flags, const int* __restrict__ only_if) {
+  if (only_if != nullptr && only_if[blockIdx.x] == 0) return;
   __shared__ double A[kCqMaxR][kCqMaxR + 1];
   __shared__ double g0[kCqMaxR];
   __shared__ double dfin[kCqMaxR];      // final pivots (0 for a dependent column)
@@ -213,10 +222,14 @@ cq_chol_kernel(double* __restrict__ ws, int r) {
   __syncthreads();
   if (tid < kCqMaxR) g0[tid] = A[tid][tid];
   __syncthreads();
+  bool weak = false;                                                // thread 0: some surviving pivot ratio < 1e-9
   for (int j = 0; j < r; ++j) {
     const double d = A[j][j];                                       // final after step j-1 (broadcast read)
     const bool alive = (g0[j] > 1e-300) && (d > 1e-12 * g0[j]);
-    if (tid == 0) dfin[j] = alive ? d : 0.0;
+    if (tid == 0) {
+      dfin[j] = alive ? d : 0.0;
+      weak = weak || (alive && d < 1e-8 * g0[j]);
+    }
     if (alive && i > j && i < r) {
       const double f = A[i][j] / d;
 #pragma unroll
@@ -240,12 +253,14 @@ cq_chol_kernel(double* __restrict__ ws, int r) {
     const double d = dfin[tid];
     dinv[tid] = d > 0.0 ? rsqrt(d) : 0.0;
   }
+  if (tid == 0 && flags != nullptr) flags[blockIdx.x] = weak ? 1 : 0;
 }
 
 // Q[row, :] = x_row . R^-1 with R = L^T:  q_j = (x_j - sum_{k<j} q_k L_jk) * dinv_j, one row per thread, fp64.
 __global__ void __launch_bounds__(kCqRows)
 cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __restrict__ Q, int64_t q_bs,
-                const double* __restrict__ ws, int m, int r) {
+                const double* __restrict__ ws, int m, int r, const int* __restrict__ only_if) {
+  if (only_if != nullptr && only_if[blockIdx.y] == 0) return;
   extern __shared__ double cq_smem[];
   double (*sL)[kCqMaxR + 1] = reinterpret_cast<double (*)[kCqMaxR + 1]>(cq_smem);   // sL[k][j] = L_jk (broadcast reads)
   double* sdinv = cq_smem + kCqMaxR * (kCqMaxR + 1);
@@ -1251,16 +1266,31 @@ int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64
       (reinterpret_cast<uintptr_t>(ws) & 7) == 0) {
     // Cholesky-QR: Gram (all SMs) -> Cholesky (one CTA per matrix) -> triangular solve per row (all SMs)
     double* wsd = static_cast<double*>(ws);
-    SOWB_CHECK_CUDA(cudaMemsetAsync(wsd, 0, size_t(batch) * kCqWsPerBatch, stream));
+    const size_t g_bytes = size_t(batch) * kCqWsPerBatch;
+    // second-pass Gram block and the per-matrix flags sit behind the first block when the workspace has room for them
+    const size_t flag_off = (2 * g_bytes + 15) & ~size_t(15);
+    const bool qr2 = ws_bytes >= flag_off + size_t(batch) * sizeof(int);
+    double* wsd2 = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + g_bytes);
+    int* flags = qr2 ? reinterpret_cast<int*>(static_cast<uint8_t*>(ws) + flag_off) : nullptr;
+    SOWB_CHECK_CUDA(cudaMemsetAsync(wsd, 0, qr2 ? 2 * g_bytes : g_bytes, stream));
     dim3 grid(ceil_div(m, kCqRows), batch);
-    cq_gram_kernel<<<grid, 256, 0, stream>>>(X, x_batch_stride, ldx, wsd, m, r);
-    SOWB_CHECK_CUDA(cudaGetLastError());
-    cq_chol_kernel<<<batch, 1024, 0, stream>>>(wsd, r);
-    SOWB_CHECK_CUDA(cudaGetLastError());
     constexpr size_t solve_smem = (kCqMaxR * (kCqMaxR + 1) + kCqMaxR) * sizeof(double) + size_t(kCqRows) * (kCqMaxR + 1) * sizeof(float);
     SOWB_CHECK_CUDA(cudaFuncSetAttribute(cq_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(solve_smem)));
-    cq_solve_kernel<<<grid, kCqRows, solve_smem, stream>>>(X, x_batch_stride, ldx, Q, q_batch_stride, wsd, m, r);
+    cq_gram_kernel<<<grid, 256, 0, stream>>>(X, x_batch_stride, ldx, wsd, m, r, nullptr);
     SOWB_CHECK_CUDA(cudaGetLastError());
+    cq_chol_kernel<<<batch, 1024, 0, stream>>>(wsd, r, flags, nullptr);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    cq_solve_kernel<<<grid, kCqRows, solve_smem, stream>>>(X, x_batch_stride, ldx, Q, q_batch_stride, wsd, m, r, nullptr);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    if (qr2) {
+      // CholeskyQR2 for the flagged matrices only: Q <- Q . chol(Q^T Q)^-T, in place
+      cq_gram_kernel<<<grid, 256, 0, stream>>>(Q, q_batch_stride, r, wsd2, m, r, flags);
+      SOWB_CHECK_CUDA(cudaGetLastError());
+      cq_chol_kernel<<<batch, 1024, 0, stream>>>(wsd2, r, nullptr, flags);
+      SOWB_CHECK_CUDA(cudaGetLastError());
+      cq_solve_kernel<<<grid, kCqRows, solve_smem, stream>>>(Q, q_batch_stride, r, Q, q_batch_stride, wsd2, m, r, flags);
+      SOWB_CHECK_CUDA(cudaGetLastError());
+    }
     return SOWB_OK;
   }
   const size_t smem = (size_t(r) + kQrWarps * 64 + size_t(kQrWarps) * 32 * 33) * sizeof(float);

@@ -266,7 +266,9 @@ def thin_qr(X: torch.Tensor, r: int) -> torch.Tensor:
     b, m, n = Xb.shape
     Q = torch.empty((b, m, r), dtype=torch.float32, device=X.device)
     # scratch: column-major CGS2 work copy (b*r*m floats) or, for r <= 64, the fp64 Gram / Cholesky block per matrix
-    work = torch.empty((max(b * r * m, b * 8448),), dtype=torch.float32, device=X.device)
+    # (r <= 64: two Gram / Cholesky blocks per matrix -- the second one for the CholeskyQR2 pass of ill-conditioned inputs --
+    # and one flag per matrix behind them)
+    work = torch.empty((max(b * r * m, 2 * b * 8448 + b + 8),), dtype=torch.float32, device=X.device)
     rc = lib.sow_thin_qr(_p(Xb), Xb.stride(0), Xb.stride(1), _p(Q), m * r, m, r, b, _p(work), work.numel() * 4,
                          _stream_ptr(X.device))
     check(rc, "sow_thin_qr")

@@ -134,3 +134,29 @@ def test_qr_weight_kernel_path_vs_reference(golden_merge):
         s = np.sign(np.diag(Qn.T @ g[f"qr/{case}/Q"]))
         assert rel_err(Qn * s, g[f"qr/{case}/Q"]) < 1e-5
         assert rel_err(Rn * s[:, None], g[f"qr/{case}/R"]) < 1e-5
+
+
+@pytest.mark.parametrize("m,r,noise", [(4096, 16, 1e-4), (4096, 64, 3e-5), (1024, 8, 1e-5)])
+def test_thin_qr_on_ill_conditioned_positive_columns(m, r, noise):
+    """The leading columns of a TT-Adam second-moment unfolding are all positive and nearly rank one (cond ~ 1e4-1e6): the
+    single-pass Cholesky-QR loses orthogonality as cond^2, so a second Cholesky-QR pass (CholeskyQR2) runs when a pivot ratio
+    trips.  Q must stay orthonormal to fp32 level and span the same space as LAPACK's Householder Q."""
+    from sow_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    u = torch.rand(m, 1, device="cuda", generator=g) + 0.5
+    v = torch.rand(1, r, device="cuda", generator=g) + 0.5
+    X = (u @ v) * (1.0 + noise * torch.rand(m, r, device="cuda", generator=g))      # positive, nearly rank one
+    Q = ops.thin_qr(X, r)
+    torch.cuda.synchronize()
+    Qd = Q.double()
+    ortho = float((Qd.T @ Qd - torch.eye(r, device="cuda", dtype=torch.float64)).abs().max())
+    assert ortho < 2e-6, ortho
+    Q_ref, _ = torch.linalg.qr(X.double())
+    resid = float((Q_ref - Qd @ (Qd.T @ Q_ref)).norm() / Q_ref.norm())                # span(Q_ref) inside span(Q)
+    assert resid < 2e-3, resid
+    # the well-conditioned case still takes the fast path and agrees with LAPACK to rounding
+    G = torch.randn(m, r, device="cuda", generator=g)
+    Qg = ops.thin_qr(G, r).double()
+    Qr, Rr = torch.linalg.qr(G.double())
+    Qr = Qr * torch.sign(torch.diagonal(Rr))
+    assert float((Qg - Qr).abs().max()) < 1e-5
