@@ -41,12 +41,23 @@
 
 namespace sowb {
 
-constexpr int kMgBM = 128, kMgBN = 128, kMgSlots = 3;   // 3 vs 4 slots measured equal: HBM, not latency, binds
+// W slots / resident B tiles per strip.  Re-measured in round 2 (Llama-350M r=50, kernel only): 3 slots + strip 4 ->
+// 0.250-0.256 ms; 4 slots + strip 3 (what fits 227 KB) -> 0.265 ms, with the load latency growing from 5.4 k to 6.5 k
+// cycles: the memory system, not the slot count, binds.  The CTAs do not finish together (globaltimer per CTA: first
+// 216 us, median 232 us, last 246 us): the remaining gap to the copy bandwidth is that tail plus start-up, i.e. a dynamic
+// tile scheduler, not more bytes in flight.
+#ifndef SOWB_MG_SLOTS
+#define SOWB_MG_SLOTS 3
+#endif
+#ifndef SOWB_MG_STRIP
+#define SOWB_MG_STRIP 4
+#endif
+constexpr int kMgBM = 128, kMgBN = 128, kMgSlots = SOWB_MG_SLOTS;
 constexpr int kMgWBytes = kMgBM * kMgBN * 2;        // 32 KB
 constexpr int kMgBBytes = 64 * kMgBN * 2;           // 16 KB
 constexpr int kMgABytes = kMgBM * 64 * 2;           // 16 KB (operand tile and staging buffer)
 constexpr int kMgSlotBytes = kMgWBytes;
-constexpr int kMgStrip = 4;                         // column tiles per strip (B tiles resident in smem)
+constexpr int kMgStrip = SOWB_MG_STRIP;             // column tiles per strip (B tiles resident in smem)
 constexpr int kMgAcc = 4;                           // TMEM accumulator stages
 // W tiles pulled into L2 (cp.async.bulk.prefetch.tensor) ahead of the slot that will load them.  OFF: measured on B200
 // (Llama-350M r=50, 20 merges each) distance 0 / 4 / 6 / 10 / 16 -> 0.250 / 0.351 / 0.366 / 0.377 / 0.379 ms: the
@@ -123,30 +134,59 @@ struct MergeCursor {
     prev_strip = -1;
     entry_changed = true;
   }
-  // [first, last] = this CTA's range of tiles
+  // [first, last] = this CTA's range of tiles.  Every role calls seek() with consecutive tile numbers, so after the first
+  // call (which locates the tile with divisions) the position is advanced incrementally: j -> mt -> strip -> entry.  The
+  // kernel is partly issue-bound (17 warps walk this cursor for every 32 KB tile), and the divisions were a quarter of
+  // its instructions.
   __device__ __forceinline__ void seek(int tile, int first, int last) {
-    bool changed = entry_changed && prev_mt < 0;   // first tile of this CTA
-    while (tile >= info[ei].tile_end) {
-      ebeg = info[ei].tile_end;
-      ++ei;
-      changed = true;
-    }
-    if (changed) {
+    bool changed = false;
+    if (prev_mt < 0) {
+      // first tile of this CTA
+      changed = entry_changed;
+      while (tile >= info[ei].tile_end) {
+        ebeg = info[ei].tile_end;
+        ++ei;
+      }
       e = &info[ei];
       g = &tab[ei];
       nt = e->n_tiles;
       mtiles = e->m_tiles;
+      const int local = tile - ebeg;
+      const int per_full = mtiles * kMgStrip;          // tiles in a full strip
+      strip = local / per_full;
+      const int rem = local - strip * per_full;
+      width = min(kMgStrip, nt - strip * kMgStrip);     // only the last strip of a matrix can be narrower
+      mt = rem / width;
+      j = rem - mt * width;
+      new_strip = true;
+      new_item = true;
+    } else {
+      new_strip = false;
+      new_item = false;
+      if (++j == width) {
+        j = 0;
+        new_item = true;
+        if (++mt == mtiles) {
+          mt = 0;
+          new_strip = true;
+          ++strip;
+          if (tile >= info[ei].tile_end) {
+            do {
+              ebeg = info[ei].tile_end;
+              ++ei;
+            } while (tile >= info[ei].tile_end);
+            changed = true;
+            e = &info[ei];
+            g = &tab[ei];
+            nt = e->n_tiles;
+            mtiles = e->m_tiles;
+            strip = 0;
+          }
+          width = min(kMgStrip, nt - strip * kMgStrip);
+        }
+      }
     }
     entry_changed = changed;
-    const int local = tile - ebeg;
-    const int per_full = mtiles * kMgStrip;          // tiles in a full strip
-    strip = local / per_full;
-    const int rem = local - strip * per_full;
-    width = min(kMgStrip, nt - strip * kMgStrip);     // only the last strip of a matrix can be narrower
-    mt = rem / width;
-    j = rem - mt * width;
-    new_strip = changed || strip != prev_strip;
-    new_item = new_strip || mt != prev_mt;
     prev_mt = mt;
     prev_strip = strip;
     last_of_item = (j == width - 1) || tile == last;
@@ -165,6 +205,11 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
   auto stamp = [&](int tile_local, int k) {
     if (dbg_ts != nullptr && blockIdx.x == 0 && tile_local < 256) dbg_ts[tile_local * 8 + k] = clock64();
   };
+  if (dbg_ts != nullptr && threadIdx.x == 0) {   // per-CTA start / end wall time (debug): dbg_ts[2048 + 2 * cta]
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg_ts[2048 + 2 * blockIdx.x] = static_cast<long long>(t);
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sBt = smem + kMgSlots * kMgSlotBytes;      // the strip's B tiles (MN-major swizzled operands)
@@ -531,6 +576,11 @@ sow_merge_kernel(const MergeDevEntry* __restrict__ tab, int n_entries, int total
   __syncthreads();
   tc_fence_after();
   if (warp == 9) tmem_dealloc(tmem_base, kMgTmemCols);
+  if (dbg_ts != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg_ts[2048 + 2 * blockIdx.x + 1] = static_cast<long long>(t);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -15,13 +15,14 @@ for fin, fout in layer_shapes(name):
 for _ in range(3):
     ops.merge_grouped(items)
 torch.cuda.synchronize()
-ts = torch.zeros(256 * 8, dtype=torch.int64, device=dev)
+ts = torch.zeros(256 * 8 + 2 * 160, dtype=torch.int64, device=dev)
 lib = _lib.load()
 lib.sow_merge_debug_timeline(ctypes.c_void_p(ts.data_ptr()))
 ops.merge_grouped(items)
 torch.cuda.synchronize()
 lib.sow_merge_debug_timeline(None)
-t = ts.view(256, 8).cpu()
+cta = ts[2048:].view(160, 2).cpu()
+t = ts[:2048].view(256, 8).cpu()
 n = int((t[:, 0] != 0).sum())
 t = t[:n] - t[0, 0]
 names = ["prod_reach", "slot_free", "epi_reach", "tfull", "W_landed", "epi_done", "store_issue", "store_read_done"]
@@ -39,3 +40,9 @@ print("avg epi wait for tfull (epi_reach -> tfull):", np.mean(mid[:, 3] - mid[:,
 print("avg epi wait for W (tfull -> W_landed):", np.mean(mid[:, 4] - mid[:, 3]))
 print("avg store (store_issue -> read_done):", np.mean(mid[:, 7] - mid[:, 6]))
 print("avg producer wait for slot:", np.mean(mid[:, 1] - mid[:, 0]))
+
+live = cta[cta[:, 0] > 0]
+t0 = int(live[:, 0].min())
+ends = sorted((live[:, 1] - t0).tolist())
+starts = sorted((live[:, 0] - t0).tolist())
+print(f"per-CTA wall time: {len(live)} CTAs, start spread {starts[-1]} ns, end min/median/max = {ends[0]}/{ends[len(ends)//2]}/{ends[-1]} ns")
