@@ -44,8 +44,10 @@ namespace sowb {
 // W slots / resident B tiles per strip.  Re-measured in round 2 (Llama-350M r=50, kernel only): 3 slots + strip 4 ->
 // 0.250-0.256 ms; 4 slots + strip 3 (what fits 227 KB) -> 0.265 ms, with the load latency growing from 5.4 k to 6.5 k
 // cycles: the memory system, not the slot count, binds.  The CTAs do not finish together (globaltimer per CTA: first
-// 216 us, median 232 us, last 246 us): the remaining gap to the copy bandwidth is that tail plus start-up, i.e. a dynamic
-// tile scheduler, not more bytes in flight.
+// 216 us, median 232 us, last 246 us): the remaining gap to the copy bandwidth is that tail plus start-up.  Giving every CTA
+// 2 / 4 / 8 interleaved sub-ranges instead of one contiguous range does not help (0.262 / 0.264 / 0.268 ms): the slow CTAs
+// are slow because of where their SM sits, not because of which addresses they touch -- only a dynamic (work-stealing)
+// tile scheduler would recover the tail.
 #ifndef SOWB_MG_SLOTS
 #define SOWB_MG_SLOTS 3
 #endif
