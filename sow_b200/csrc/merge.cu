@@ -46,8 +46,11 @@ namespace sowb {
 // cycles: the memory system, not the slot count, binds.  The CTAs do not finish together (globaltimer per CTA: first
 // 216 us, median 232 us, last 246 us): the remaining gap to the copy bandwidth is that tail plus start-up.  Giving every CTA
 // 2 / 4 / 8 interleaved sub-ranges instead of one contiguous range does not help (0.262 / 0.264 / 0.268 ms): the slow CTAs
-// are slow because of where their SM sits, not because of which addresses they touch -- only a dynamic (work-stealing)
-// tile scheduler would recover the tail.
+// are slow because of where their SM sits, not because of which addresses they touch.  A work-stealing scheduler was
+// built and measured as well (static first range + 8-tile chunks claimed with an atomic counter, published by the producer
+// to the other roles through an smem ring): it balances the tail (0.272 -> 0.260 ms in that build) but the extra live state
+// pushes the 18-warp kernel past its 96-register budget (5 warps share a 16 K-register sub-partition, so 96 is the cap;
+// 64 B of spills in the epilogue loop) and the steady state loses more (0.253 -> 0.272 ms) than the tail gains.
 #ifndef SOWB_MG_SLOTS
 #define SOWB_MG_SLOTS 3
 #endif
