@@ -147,14 +147,21 @@ int sow_merge_grouped(const sowb_merge_entry* entries_host, int n, int dtype, vo
  * Batched: `batch` matrices, strides in elements.  Sign convention: R has non-negative diagonal.
  */
 int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64_t q_batch_stride, int m, int r,
-                int batch, void* ws /* >= batch*m*r*4 bytes */, size_t ws_bytes, void* stream);
+                int batch, void* ws /* sow_thin_qr_workspace_bytes(m, r, batch), 16-byte aligned */, size_t ws_bytes,
+                void* stream);
+/* scratch of sow_thin_qr: Cholesky factors, per-matrix flags and the fp64 Gram partials (summed in a fixed order: the
+ * factorisation is bit-reproducible run to run) for r <= 64; batch*m*r*4 bytes for the Gram-Schmidt path above that. */
+size_t sow_thin_qr_workspace_bytes(int m, int r, int batch);
 
 /*
  * TT projection  R[r,n] = Q[m,r]^T . L[m,n]  in fp32 (3xTF32-free, exact fp32 FMA accumulate).
  * Replaces R[:right_rank,:] of the complete QR in tn_gradient/tt.py:129-133.  Batched like sow_thin_qr.
  */
 int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q_batch_stride, float* R,
-               int64_t r_batch_stride, int m, int n, int r, int batch, void* stream);
+               int64_t r_batch_stride, int m, int n, int r, int batch, void* ws, size_t ws_bytes, void* stream);
+/* scratch of tt_project: when the m rows are split over CTAs each split stores a partial [r x n] and the partials are
+ * summed in split order (bit-reproducible; no atomics).  0 when one split suffices (ws may then be NULL). */
+size_t tt_project_workspace_bytes(int m, int n, int r, int batch);
 
 /*
  * Fused pad + interleave for TensorTrain.from_matrix / from_tensor (tn_gradient/tt.py:48-67,33; utils.py:78-84),
@@ -174,7 +181,9 @@ int tt_deinterleave(const float* src, int M, int N, int mm, int nn, int order, v
  *   tt_reconstruct2 : dst[M, N] = (G1[P, r] . G2[r, P]) de-interleaved and un-padded   (TensorTrain.to_matrix, tt.py:242-247)
  */
 int tt_gather2(const void* src, int M, int N, int mm, int nn, float* X, int ncols, int dtype, void* stream);
-int tt_project2(const void* src, int M, int N, int mm, int nn, const float* Q, float* R, int r, int dtype, void* stream);
+int tt_project2(const void* src, int M, int N, int mm, int nn, const float* Q, float* R, int r, int dtype, void* ws,
+                size_t ws_bytes, void* stream);
+size_t tt_project2_workspace_bytes(int mm, int nn, int r);   /* split partials, as tt_project_workspace_bytes */
 int tt_reconstruct2(const float* G1, const float* G2, int r, void* dst, int M, int N, int mm, int nn, int dtype, void* stream);
 
 /* fp32 C[m,n] = A[m,r] . B[r,n] with small r: one link of the reconstruction chain (tt.py:213-237). */
@@ -202,8 +211,9 @@ int tt_adam_fused2(void* p, const void* g, const float* G1m, const float* G2m, c
  *   1. tt_adam2_head  : X{m,v}[P, 64] = the first 64 columns of the NEW moments (interleaved layout, P = mm*nn).
  *                       p is not modified.
  *   2. sow_thin_qr    : Q'{m,v}[P, r] from the first r columns of X{m,v}      (caller, batch = 2, ldx = 64)
- *   3. tt_adam2_fused : Adam update of p  +  R'{m,v}[r, P] += Q'^T . (new moments), accumulated tile by tile in
- *                       registers; R' must be zero-filled by the caller (fp32 red.add across row ranges).
+ *   3. tt_adam2_fused : Adam update of p  +  R'{m,v}[r, P] = Q'^T . (new moments), accumulated tile by tile in
+ *                       registers; each row range stores a partial in ws and the partials are summed in range order
+ *                       (bit-reproducible; no atomics).  ws: tt_adam2_fused_workspace_bytes(mm, nn) bytes.
  * New cores: G1' = Q' (P x r), G2' = R' (r x P).  r <= 64.  first_step != 0 -> previous moments are zero.
  */
 int tt_adam2_head(const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r, float* Xm,
@@ -211,7 +221,9 @@ int tt_adam2_head(const void* g, const float* G1m, const float* G2m, const float
                   void* stream);
 int tt_adam2_fused(void* p, const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r,
                    const float* Qm, const float* Qv, float* Rm, float* Rv, int M, int N, int mm, int nn, double beta1,
-                   double beta2, double eps, double step_size, double lr_wd, int first_step, int dtype, void* stream);
+                   double beta2, double eps, double step_size, double lr_wd, int first_step, int dtype, void* ws,
+                   size_t ws_bytes, void* stream);
+size_t tt_adam2_fused_workspace_bytes(int mm, int nn);
 
 /*
  * The whole order-2 TT-Adam step in one call, with both rank-r products on the tensor cores (tcgen05, operands split

@@ -76,16 +76,21 @@ SIGNATURES = {
     "sow_merge_table_stride": (_sz, []),
     "sow_merge_grouped": (_i, [ctypes.POINTER(MergeEntry), _i, _i, _vp, _sz, _vp]),
     "sow_thin_qr": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp, _sz, _vp]),
-    "tt_project": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "sow_thin_qr_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tt_project": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "tt_project_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tt_interleave": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "tt_deinterleave": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "tt_gather2": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
-    "tt_project2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "tt_project2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "tt_project2_workspace_bytes": (_sz, [_i, _i, _i]),
     "tt_reconstruct2": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "tt_matmul_rk": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "tt_adam_fused2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i, _vp]),
     "tt_adam2_head": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _vp]),
-    "tt_adam2_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i, _vp]),
+    "tt_adam2_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i,
+                            _vp, _sz, _vp]),
+    "tt_adam2_fused_workspace_bytes": (_sz, [_i, _i]),
     "tt_adam2_workspace_bytes": (_sz, [_i, _i]),
     "tt_adam2_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i,
                            _vp, _sz, _vp]),

@@ -1,5 +1,6 @@
 #include "common.cuh"
 
+#include <map>
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -16,6 +17,25 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+cudaError_t set_max_smem_once(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;     // (device, kernel) -> largest size already set
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find({dev, kernel});
+    if (dev >= 0 && it != done.end() && it->second >= bytes) return cudaSuccess;
+  }
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e == cudaSuccess && dev >= 0) {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& slot = done[{dev, kernel}];
+    slot = std::max(slot, bytes);
+  }
+  return e;
 }
 
 int num_sms() {
@@ -255,6 +275,6 @@ int sow_profile_read(int klass, double* total_ms, double* total_work, int64_t* l
   if (launches) *launches = n;
   return SOWB_OK;
 }
-int sow_abi_version(void) { return 2; }
+int sow_abi_version(void) { return 3; }
 const char* sow_last_error(void) { return sowb::g_err; }
 }

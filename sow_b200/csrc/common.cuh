@@ -27,10 +27,44 @@ int set_error(int code, const char* fmt, ...);
     if (!(cond)) return ::sowb::set_error(SOWB_EINVAL, __VA_ARGS__); \
   } while (0)
 
+// Programmatic dependent launch: the chains of small dependent kernels on the TT path (head -> Gram -> sum -> Cholesky ->
+// solve -> ... ) spend as long in launch gaps as in the kernels.  Launched through launch_pdl, a kernel may be scheduled
+// while its predecessor in the stream drains; pdl_wait() -- the first statement that touches global memory must come
+// after it -- blocks until the predecessor has completed and its writes are visible, so the stream order is unchanged.
+// Both instructions are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): ~1 us of host time on every launch otherwise.
+cudaError_t set_max_smem_once(const void* kernel, size_t bytes);
+template <typename K>
+inline cudaError_t set_max_smem_once(K* kernel, size_t bytes) {
+  return set_max_smem_once(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 // Number of SMs of the current device (cached per device).
 int num_sms();
 // 0 if the current device is sm_100, else an error code (message set).
 int require_sm100();
+// dst[b][i] = sum over s (ascending) of part[b][s][i]: the fixed-order reduction of split partials (tt.cu)
+int launch_sum_splits(const float* part, int splits, int64_t split_stride, int64_t part_bs, float* dst, int64_t dst_bs,
+                      int64_t n, int batch, cudaStream_t stream);
 
 // Bind the primary context of the device owning `ptr` to the calling thread if the thread has none (see common.cu).
 int ensure_context_for(const void* ptr);

@@ -212,7 +212,7 @@ static int launch_gemm(const Segment* segs, int nseg, void* C_bf16, float* C_f32
   const int total = p.m_tiles * p.n_tiles * p.splits;
   if (total <= 0 || kb_total <= 0) return SOWB_OK;
   auto kern = sow_gemm_kernel<BN, A_MN, B_MN, EPI, MT>;
-  SOWB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  SOWB_CHECK_CUDA(set_max_smem_once(kern, size_t(S::kTotal)));
   const int grid = total < sms ? total : sms;
   ProfileScope prof(stream, prof_class, alg_flops);   // algorithmic flops: un-padded ranks
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(maps, p);
@@ -281,7 +281,7 @@ static int k2_max_clusters(int G) {
   std::lock_guard<std::mutex> lk(mu);
   if (cache[dev][G] == 0) {
     int n = 0;
-    cudaFuncSetAttribute(sow_k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemTotal);
+    set_max_smem_once(sow_k2_kernel, size_t(kK2SmemTotal));
     if (G > 8) cudaFuncSetAttribute(sow_k2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G * 64);
@@ -517,7 +517,7 @@ int sow_group_bwd(const void* x, const void* A_cat, const void* t_cat, const sow
   const int Ti = static_cast<int>(T);
 
   // ---- K2: one pass over every dY_i -> dt_i (into dt_cat) and the split partials of dB_i^T -------------
-  SOWB_CHECK_CUDA(cudaFuncSetAttribute(sow_k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemTotal));
+  SOWB_CHECK_CUDA(set_max_smem_once(sow_k2_kernel, size_t(kK2SmemTotal)));
   K2Plan plans[kMaxGroup];
   bool uniform = true;
   for (int i = 0; i < n; ++i) {

@@ -790,7 +790,7 @@ int sow_merge_grouped(const sowb_merge_entry* entries, int n, int dtype, void* t
   if (table_bytes < size_t(n) * sizeof(MergeDevEntry))
     return set_error(SOWB_EWORKSPACE, "sow_merge_grouped: table %zu B < required %zu B", table_bytes,
                      size_t(n) * sizeof(MergeDevEntry));
-  SOWB_CHECK_CUDA(cudaFuncSetAttribute(sow_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmemTotal));
+  SOWB_CHECK_CUDA(set_max_smem_once(sow_merge_kernel, size_t(kMgSmemTotal)));
   const int sms = num_sms();
   // ranks above 64 are applied as successive 64-wide chunks (W_prev = W after the first chunk)
   for (int chunk = 0; chunk < max_chunks; ++chunk) {

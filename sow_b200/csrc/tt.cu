@@ -160,52 +160,91 @@ constexpr int kCqMaxR = 64;
 constexpr int kCqRows = 128;
 constexpr size_t kCqWsPerBatch = (kCqMaxR * kCqMaxR + kCqMaxR) * sizeof(double);
 
+// Gram partials: CTA (x, b) accumulates X_b[rows]^T X_b[rows] in fp64 over the 128-row blocks x, x + gridDim.x, ... (fixed
+// order) and stores the lower triangle compactly, part[(b * gridDim.x + x)][i * r + j].  cq_sum_kernel adds the
+// partials in block order, so the whole factorisation is bit-reproducible (no fp64 atomics).
+// RT = ceil(r / 16): a thread owns the RT x RT entries G[ty + 16a][tx + 16c] (r = 8: one fp64 FMA and two conversions per
+// row instead of 16 + 8 -- the f32 -> f64 conversions, not the FMAs, bound the untemplated loop)
+template <int RT>
 __global__ void __launch_bounds__(256)
-cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __restrict__ ws, int m, int r,
+cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __restrict__ part, int m, int r,
                const int* __restrict__ only_if) {
+  pdl_trigger();
+  pdl_wait();
   if (only_if != nullptr && only_if[blockIdx.y] == 0) return;      // second pass: flagged matrices only
   __shared__ float sx[kCqRows][kCqMaxR + 1];
   const float* Xb = X + blockIdx.y * x_bs;
-  double* G = ws + blockIdx.y * (kCqMaxR * kCqMaxR + kCqMaxR);
-  const int row0 = blockIdx.x * kCqRows;
-  const int rows = min(kCqRows, m - row0);
+  double* G = part + (static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x) * (r * r);
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < rows * r; idx += 256) {
-    const int i = idx / r, k = idx - i * r;
-    sx[i][k] = Xb[static_cast<int64_t>(row0 + i) * ldx + k];
-  }
-  __syncthreads();
   const int ty = tid >> 4, tx = tid & 15;   // G[ty + 16a][tx + 16c]
-  double acc[4][4];
+  double acc[RT][RT];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < RT; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-  for (int i = 0; i < rows; ++i) {
-    double xa[4], xc[4];
+    for (int c = 0; c < RT; ++c) acc[a][c] = 0.0;
+  for (int row0 = blockIdx.x * kCqRows; row0 < m; row0 += gridDim.x * kCqRows) {
+    const int rows = min(kCqRows, m - row0);
+    __syncthreads();
+    for (int idx = tid; idx < rows * r; idx += 256) {
+      const int i = idx / r, k = idx - i * r;
+      sx[i][k] = Xb[static_cast<int64_t>(row0 + i) * ldx + k];
+    }
+    __syncthreads();
+    for (int i = 0; i < rows; ++i) {
+      double xa[RT], xc[RT];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) xa[a] = (ty + 16 * a < r) ? static_cast<double>(sx[i][ty + 16 * a]) : 0.0;
+      for (int a = 0; a < RT; ++a) xa[a] = (ty + 16 * a < r) ? static_cast<double>(sx[i][ty + 16 * a]) : 0.0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) xc[c] = (tx + 16 * c < r) ? static_cast<double>(sx[i][tx + 16 * c]) : 0.0;
+      for (int c = 0; c < RT; ++c) xc[c] = (tx + 16 * c < r) ? static_cast<double>(sx[i][tx + 16 * c]) : 0.0;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < RT; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][c] = fma(xa[a], xc[c], acc[a][c]);
+        for (int c = 0; c < RT; ++c) acc[a][c] = fma(xa[a], xc[c], acc[a][c]);
+    }
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < RT; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < RT; ++c) {
       const int i = ty + 16 * a, j = tx + 16 * c;
-      if (i < r && j < r && j <= i) atomicAdd(&G[i * kCqMaxR + j], acc[a][c]);   // lower triangle is enough
+      if (i < r && j < r && j <= i) G[i * r + j] = acc[a][c];   // lower triangle is enough
     }
+}
+
+// G[i][j] (lower triangle of the matrix's 64 x 64 block) = sum of its Gram partials in block order: one entry per thread,
+// the loads of eight partials in flight at a time.  grid (ceil(r*r / 256), batch)
+__global__ void __launch_bounds__(256)
+cq_sum_kernel(const double* __restrict__ part, int n_part, int r, double* __restrict__ ws, const int* __restrict__ only_if) {
+  pdl_trigger();
+  pdl_wait();
+  if (only_if != nullptr && only_if[blockIdx.y] == 0) return;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  const int rr = r * r;
+  if (e >= rr) return;
+  const int i = e / r, j = e - i * r;
+  if (j > i) return;
+  const double* pp = part + static_cast<int64_t>(blockIdx.y) * n_part * rr + e;
+  double g = 0.0;
+  int q = 0;
+  for (; q + 8 <= n_part; q += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = pp[static_cast<int64_t>(q + u) * rr];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) g += v[u];
+  }
+  for (; q < n_part; ++q) g += pp[static_cast<int64_t>(q) * rr];
+  ws[blockIdx.y * (kCqMaxR * kCqMaxR + kCqMaxR) + i * kCqMaxR + j] = g;
 }
 
 // In place: lower triangle of G -> L; dinv[j] = 1 / L_jj (0 for a dependent column).  1024 threads, 4 entries each.
 // Right-looking Cholesky with the column scaling deferred: step j only needs the pivot d_j = A[j][j] and the unscaled
 // column j, A[i][k] -= A[i][j] A[k][j] / d_j, so there is ONE barrier per step; L = A . diag(d)^-1/2 at the end.
 __global__ void __launch_bounds__(1024)
-cq_chol_kernel(double* __restrict__ ws, int r, int* __restrict__ flags, const int* __restrict__ only_if) {
+cq_chol_kernel(double* __restrict__ ws, const double* __restrict__ part, int n_part, int r, int* __restrict__ flags,
+               const int* __restrict__ only_if) {
+  pdl_trigger();
+  pdl_wait();
   if (only_if != nullptr && only_if[blockIdx.x] == 0) return;
   __shared__ double A[kCqMaxR][kCqMaxR + 1];
   __shared__ double g0[kCqMaxR];
@@ -217,7 +256,26 @@ cq_chol_kernel(double* __restrict__ ws, int r, int* __restrict__ flags, const in
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int k = kb + 16 * c;
-    A[i][k] = (i < r && k <= i) ? G[i * kCqMaxR + k] : 0.0;
+    double g = 0.0;
+    if (i < r && k <= i) {
+      if (part == nullptr) {
+        g = G[i * kCqMaxR + k];
+      } else {
+        // small ranks: the fixed-order sum of the Gram partials happens here (no separate cq_sum_kernel launch)
+        const int rr = r * r;
+        const double* pp = part + static_cast<int64_t>(blockIdx.x) * n_part * rr + i * r + k;
+        int q = 0;
+        for (; q + 8 <= n_part; q += 8) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = pp[static_cast<int64_t>(q + u) * rr];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) g += v[u];
+        }
+        for (; q < n_part; ++q) g += pp[static_cast<int64_t>(q) * rr];
+      }
+    }
+    A[i][k] = g;
   }
   __syncthreads();
   if (tid < kCqMaxR) g0[tid] = A[tid][tid];
@@ -257,9 +315,14 @@ cq_chol_kernel(double* __restrict__ ws, int r, int* __restrict__ flags, const in
 }
 
 // Q[row, :] = x_row . R^-1 with R = L^T:  q_j = (x_j - sum_{k<j} q_k L_jk) * dinv_j, one row per thread, fp64.
+// RQ = r rounded up to 8 / 16 / 32 / 64 bounds the unrolled substitution (the r = 8 instance is 28 FMAs, not a walk through
+// the 2016-FMA code of the r = 64 one).
+template <int RQ>
 __global__ void __launch_bounds__(kCqRows)
 cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __restrict__ Q, int64_t q_bs,
                 const double* __restrict__ ws, int m, int r, const int* __restrict__ only_if) {
+  pdl_trigger();
+  pdl_wait();
   if (only_if != nullptr && only_if[blockIdx.y] == 0) return;
   extern __shared__ double cq_smem[];
   double (*sL)[kCqMaxR + 1] = reinterpret_cast<double (*)[kCqMaxR + 1]>(cq_smem);   // sL[k][j] = L_jk (broadcast reads)
@@ -282,9 +345,9 @@ cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __res
   }
   __syncthreads();
   if (tid < rows) {
-    double q[kCqMaxR];
+    double q[RQ];
 #pragma unroll
-    for (int j = 0; j < kCqMaxR; ++j) {
+    for (int j = 0; j < RQ; ++j) {
       q[j] = 0.0;
       if (j < r) {
         // four independent partial sums: the fp64 FMA chain is latency-bound with one row per thread
@@ -300,7 +363,7 @@ cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __res
       }
     }
 #pragma unroll
-    for (int j = 0; j < kCqMaxR; ++j)
+    for (int j = 0; j < RQ; ++j)
       if (j < r) sx[tid][j] = static_cast<float>(q[j]);
   }
   __syncthreads();
@@ -311,8 +374,31 @@ cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// projection R[r, n] = Q[m, r]^T L[m, n]    (fp32, register-tiled; split over m with fp32 red.add)
+// projection R[r, n] = Q[m, r]^T L[m, n]    (fp32, register-tiled; split over m into per-split partials that
+// sum_splits_kernel adds in split order: bit-reproducible, no atomics)
 // ------------------------------------------------------------------------------------------------
+// dst[b][i] = sum_s part[b][s][i], s ascending (fixed order).  grid (blocks, batch)
+__global__ void sum_splits_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int64_t part_bs,
+                                  float* __restrict__ dst, int64_t dst_bs, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
+  const float* pb = part + blockIdx.y * part_bs;
+  float* db = dst + blockIdx.y * dst_bs;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    float s = pb[i];
+#pragma unroll 4
+    for (int k = 1; k < splits; ++k) s += pb[k * split_stride + i];
+    db[i] = s;
+  }
+}
+
+int launch_sum_splits(const float* part, int splits, int64_t split_stride, int64_t part_bs, float* dst, int64_t dst_bs,
+                      int64_t n, int batch, cudaStream_t stream) {
+  const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, int64_t(num_sms()) * 8));
+  SOWB_CHECK_CUDA(launch_pdl(sum_splits_kernel, dim3(blocks, batch), dim3(256), 0, stream, part, splits, split_stride, part_bs, dst, dst_bs, n));
+  return SOWB_OK;
+}
+
 constexpr int kPjTN = 128;   // columns of L per CTA
 constexpr int kPjTM = 32;    // rows of L per smem stage
 constexpr int kPjThreads = 256;
@@ -323,13 +409,13 @@ constexpr int kPjRT = 64;    // rank tile
 // (3 LDS.128 per 32 FMA: FMA-bound, not LDS-bound).  The next K stage is prefetched into registers during the FMAs.
 __global__ void __launch_bounds__(kPjThreads)
 tt_project_kernel(const float* __restrict__ L, int64_t l_bs, const float* __restrict__ Q, int64_t q_bs,
-                  float* __restrict__ R, int64_t r_bs, int m, int n, int r, int m_per_split) {
+                  float* __restrict__ R, int64_t r_bs, int64_t split_stride, int m, int n, int r, int m_per_split) {
   __shared__ __align__(16) float sL[kPjTM][kPjTN];
   __shared__ __align__(16) float sQ[kPjTM][kPjRT];
   const int b = blockIdx.z;
   const float* Lb = L + b * l_bs;
   const float* Qb = Q + b * q_bs;
-  float* Rb = R + b * r_bs;
+  float* Rb = R + b * r_bs + blockIdx.y * split_stride;   // split s stores its own partial (split_stride 0: one split)
   const int n0 = blockIdx.x * kPjTN;
   const int m_begin = blockIdx.y * m_per_split;
   const int m_end = min(m, m_begin + m_per_split);
@@ -411,10 +497,7 @@ tt_project_kernel(const float* __restrict__ L, int64_t l_bs, const float* __rest
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int gc = n0 + (c < 4 ? tn * 4 + c : 64 + tn * 4 + (c - 4));
-        if (gc < n) {
-          if (gridDim.y == 1) Rb[static_cast<int64_t>(gr) * n + gc] = acc[a][c];
-          else atomicAdd(&Rb[static_cast<int64_t>(gr) * n + gc], acc[a][c]);
-        }
+        if (gc < n) Rb[static_cast<int64_t>(gr) * n + gc] = acc[a][c];
       }
     }
   }
@@ -580,10 +663,11 @@ __global__ void tt_gather2_kernel(const T* __restrict__ src, int M, int N, int m
 template <typename T>
 __global__ void __launch_bounds__(kPjThreads)
 tt_project2_kernel(const T* __restrict__ src, int M, int N, int mm, int nn, const float* __restrict__ Q,
-                   float* __restrict__ R, int r, int m_per_split) {
+                   float* __restrict__ R, int64_t split_stride, int r, int m_per_split) {
   __shared__ __align__(16) float sL[kPjTM][kPjTN];
   __shared__ __align__(16) float sQ[kPjTM][kPjRT];
   __shared__ int64_t s_colpart[kPjTN];
+  float* Rs = R + blockIdx.y * split_stride;   // split s stores its own partial (split_stride 0: one split)
   __shared__ int s_coli2[kPjTN], s_colo2[kPjTN];
   const int P = mm * nn;
   const int n0 = blockIdx.x * kPjTN;
@@ -670,10 +754,7 @@ tt_project2_kernel(const T* __restrict__ src, int M, int N, int mm, int nn, cons
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int gc = n0 + (c < 4 ? tn * 4 + c : 64 + tn * 4 + (c - 4));
-        if (gc < P) {
-          if (gridDim.y == 1) R[static_cast<int64_t>(gr) * P + gc] = acc[a][c];
-          else atomicAdd(&R[static_cast<int64_t>(gr) * P + gc], acc[a][c]);
-        }
+        if (gc < P) Rs[static_cast<int64_t>(gr) * P + gc] = acc[a][c];
       }
     }
   }
@@ -878,7 +959,7 @@ tt_adam_fused2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* _
 // HEAD : the first 64 columns of m', v' (P x 64 each) -> X, the input of the thin QR.  p is NOT touched.
 // FULL : CTA = (strip of 64 columns, range of 64-row tiles).  Per tile: reconstruct the old moments from the cores
 //        (register-tiled rank-R product), Adam on p, stash m', v' in shared memory, accumulate R'[:, strip] +=
-//        Q'[tile rows]^T . tile in registers; one fp32 red.add of the accumulators per CTA at the end.
+//        Q'[tile rows]^T . tile in registers; the accumulators are stored once per CTA as its row-range's partial (summed in range order afterwards).
 // Traffic per step: g once + p read/write + cores (vs. + 16 B/element for dense fp32 moments written and re-read).
 // R = rank padded to 8/16/32/64 (cores and bases are zero-padded in shared memory).
 // ------------------------------------------------------------------------------------------------
@@ -888,10 +969,12 @@ tt_adam2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __restr
                 const float* __restrict__ G1v, const float* __restrict__ G2v, int r, const float* __restrict__ Qm,
                 const float* __restrict__ Qv, float* __restrict__ Rm, float* __restrict__ Rv, float* __restrict__ Xm,
                 float* __restrict__ Xv, int M, int N, int mm, int nn, float beta1, float omb1, float beta2, float omb2,
-                float eps, float step_size, float lr_wd, int first_step, int tiles_per_cta) {
+                float eps, float step_size, float lr_wd, int first_step, int tiles_per_cta, int64_t split_stride) {
   extern __shared__ __align__(16) float fs[];
   const int P = mm * nn;
   float* s2m = fs;                 // [R][64]  G2m[k][b0 + c]
+  pdl_trigger();
+  pdl_wait();
   float* s2v = s2m + R * 64;
   float* s1m = s2v + R * 64;       // [64][R]  G1m[a0 + i][k]
   float* s1v = s1m + R * 64;
@@ -1099,9 +1182,339 @@ tt_adam2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __restr
     for (int k = 0; k < KQ; ++k) {
       const int gk = kpart * KQ + k;
       if (gk < r) {
-        atomicAdd(Rm + static_cast<int64_t>(gk) * P + b0 + pcol, accm[k]);
-        atomicAdd(Rv + static_cast<int64_t>(gk) * P + b0 + pcol, accv[k]);
+        // row-range split blockIdx.y stores its own partial (split_stride 0: one split, Rm / Rv are the results)
+        Rm[blockIdx.y * split_stride + static_cast<int64_t>(gk) * P + b0 + pcol] = accm[k];
+        Rv[blockIdx.y * split_stride + static_cast<int64_t>(gk) * P + b0 + pcol] = accv[k];
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FULL step for ranks <= 16 with the projection accumulated in REGISTERS (tt_adam2_reg_kernel).
+//
+// The kernel above stashes every m' / v' tile in shared memory and re-reads it column by column for the projection
+// (256 shared loads per 256 FMAs per thread and tile: the shared-memory pipe bounds it, ~4500 cycles per 64 x 64 tile).
+// Here a thread keeps its (RTH rows x CT columns) micro-tile of m', v' in registers after the Adam update and multiplies
+// it straight into its own accumulators acc[k][c] += Q'[row, k] . m'[row, c] for ALL k, over every tile of the CTA's
+// row range; the TY threads that share a column group are summed once, through shared memory, when the range is done
+// (fixed order).  Shared loads per tile: the G1 / Q' rows (warp-broadcast LDS.128) and the G2 strip (CT-wide) only.
+//   R =  8: CT = 4 (TY = 16, RTH = 2) ; R = 16: CT = 2 (TY = 8, RTH = 4)   [R = 32, CT = 1 measured 260 us at 4096^2
+//   against 185 us for the tensor-core kernel: not instantiated]
+//   -> 2 . R . CT = 64 accumulators per thread in every configuration; tile = 32 rows x 64 columns.
+// G1 / Q' tiles are staged by cp.async, three buffers deep (one barrier per tile); g and p of the tile are requested
+// before the barrier and consumed after the reconstruction FMAs.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CT>
+struct RawVec;
+template <>
+struct RawVec<__nv_bfloat16, 4> { using type = uint2; };
+template <>
+struct RawVec<__nv_bfloat16, 2> { using type = uint32_t; };
+template <>
+struct RawVec<__nv_bfloat16, 1> { using type = unsigned short; };
+template <>
+struct RawVec<float, 4> { using type = float4; };
+template <>
+struct RawVec<float, 2> { using type = float2; };
+template <>
+struct RawVec<float, 1> { using type = float; };
+
+template <typename T, int CT>
+__device__ __forceinline__ void raw_unpack(const typename RawVec<T, CT>::type& raw, float (&v)[CT]) {
+  T tmp[CT];
+  memcpy(tmp, &raw, sizeof(tmp));
+#pragma unroll
+  for (int c = 0; c < CT; ++c) v[c] = load_as_f32<T>(tmp, c);
+}
+template <typename T, int CT>
+__device__ __forceinline__ typename RawVec<T, CT>::type raw_pack(const float (&v)[CT]) {
+  T tmp[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) store_from_f32<T>(tmp, c, v[c]);
+  typename RawVec<T, CT>::type raw;
+  memcpy(&raw, tmp, sizeof(tmp));
+  return raw;
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* src, bool valid) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled, the source is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int CT>
+__device__ __forceinline__ void lds_ct(const float* s, float (&v)[CT]) {
+  if constexpr (CT == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(s);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  } else if constexpr (CT == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(s);
+    v[0] = t.x, v[1] = t.y;
+  } else {
+    v[0] = s[0];
+  }
+}
+template <int CT>
+__device__ __forceinline__ void sts_ct(float* s, const float (&v)[CT]) {
+  if constexpr (CT == 4) *reinterpret_cast<float4*>(s) = make_float4(v[0], v[1], v[2], v[3]);
+  else if constexpr (CT == 2) *reinterpret_cast<float2*>(s) = make_float2(v[0], v[1]);
+  else s[0] = v[0];
+}
+
+constexpr int kRegTileRows = 32;
+constexpr size_t reg_kernel_smem(int R) { return std::max<size_t>(size_t(2048) * R, 32768); }
+
+template <typename T, int R, int CT>
+__global__ void __launch_bounds__(256, 2)
+tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __restrict__ G1m, const float* __restrict__ G2m,
+                    const float* __restrict__ G1v, const float* __restrict__ G2v, int r, const float* __restrict__ Qm,
+                    const float* __restrict__ Qv, float* __restrict__ Rm, float* __restrict__ Rv, int M, int N, int mm, int nn,
+                    float beta1, float omb1, float beta2, float omb2, float eps, float step_size, float lr_wd, int first_step,
+                    int tiles_per_cta, int64_t split_stride) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int TX = 64 / CT, TY = 256 / TX, RTH = kRegTileRows / TY;
+  constexpr int KS = (CT == 4) ? 2 : 4;       // k-step of the reconstruction: 2 . KS . CT operand registers
+  static_assert(2 * R * CT == 64 && TY * R * 64 == 8192, "micro-tile shape");
+  constexpr int kArr = kRegTileRows * R;        // floats of one staged array (32 rows x R)
+  constexpr int kBuf = 4 * kArr;                // G1m | G1v | Q'm | Q'v
+  using Raw = typename RawVec<T, CT>::type;
+  extern __shared__ __align__(16) float fs[];
+  float* s2m = fs;                 // [R][64]  G2m[k][b0 + c]
+  float* s2v = s2m + R * 64;
+  float* stage = s2v + R * 64;     // [3][4][32][R]
+  const int P = mm * nn;
+  const int tid = threadIdx.x, ty = tid / TX, tx = tid % TX;
+  const int b0 = blockIdx.x * 64;
+  const int n_tiles = (P + kRegTileRows - 1) / kRegTileRows;
+  const int t_begin = blockIdx.y * tiles_per_cta;
+  const int t_end = min(n_tiles, t_begin + tiles_per_cta);
+
+  float accm[R][CT], accv[R][CT];
+#pragma unroll
+  for (int k = 0; k < R; ++k)
+#pragma unroll
+    for (int c = 0; c < CT; ++c) accm[k][c] = accv[k][c] = 0.f;
+
+  // column part of the index map (strip-constant): gb = i2 * nn + o2 -> source (row offset i2, column offset o2).
+  // A thread's CT columns cross at most one i2 boundary (nn >= CT is required by the launcher): columns c >= cut sit
+  // in the next i2 block, i.e. one source row further down and nn columns to the left.
+  const int gb0 = b0 + tx * CT;
+  const int ci2 = gb0 / nn, co2 = gb0 - ci2 * nn;
+  const int cut = nn - co2;                                    // >= CT: no boundary inside the thread's columns
+  const int ncols = min(CT, P - gb0);                          // columns c < ncols exist in the unfolding (<= 0: none)
+  const bool vec_base = cut >= CT && ncols >= CT &&
+                        ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) % sizeof(Raw)) == 0;
+
+  // rows (a0 + i) of the four [P x r] arrays -> stage buffer; cp.async when the rows are whole 16-byte chunks
+  const bool fast = (r == R) && (((reinterpret_cast<uintptr_t>(Qm) | reinterpret_cast<uintptr_t>(Qv) |
+                                   reinterpret_cast<uintptr_t>(G1m) | reinterpret_cast<uintptr_t>(G1v)) & 15) == 0);
+  auto stage_tile = [&](int t, float* buf) {
+    const int a0 = t * kRegTileRows;
+    constexpr int kChunks = kBuf / 4;            // 16-byte chunks of one buffer
+    if (fast) {
+#pragma unroll
+      for (int u = 0; u < kChunks / 256; ++u) {
+        const int q = tid + u * 256;
+        const int arr = q / (kArr / 4), w = q - arr * (kArr / 4);
+        const int i = w / (R / 4), k4 = w - i * (R / 4);
+        if (first_step && arr < 2) continue;
+        const float* base = arr == 0 ? G1m : (arr == 1 ? G1v : (arr == 2 ? Qm : Qv));
+        const bool ok = a0 + i < P;
+        cp_async16(buf + arr * kArr + i * R + k4 * 4, ok ? base + static_cast<int64_t>(a0 + i) * r + k4 * 4 : base, ok);
+      }
+    } else {
+      for (int q = tid; q < kBuf; q += 256) {
+        const int arr = q / kArr, w = q - arr * kArr;
+        const int i = w / R, k = w - i * R;
+        if (first_step && arr < 2) continue;
+        const float* base = arr == 0 ? G1m : (arr == 1 ? G1v : (arr == 2 ? Qm : Qv));
+        buf[q] = (a0 + i < P && k < r) ? base[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+      }
+    }
+  };
+
+  if (t_begin < t_end) stage_tile(t_begin, stage);
+  cp_async_commit();
+  if (!first_step) {
+    for (int idx = tid; idx < R * 64; idx += 256) {
+      const int kk = idx / 64, c = idx % 64;
+      const bool ok = kk < r && b0 + c < P;
+      s2m[idx] = ok ? G2m[static_cast<int64_t>(kk) * P + b0 + c] : 0.f;
+      s2v[idx] = ok ? G2v[static_cast<int64_t>(kk) * P + b0 + c] : 0.f;
+    }
+  }
+
+  for (int t = t_begin; t < t_end; ++t) {
+    const int a0 = t * kRegTileRows;
+    float* buf = stage + ((t - t_begin) % 3) * kBuf;
+    if (t + 1 < t_end) stage_tile(t + 1, stage + ((t + 1 - t_begin) % 3) * kBuf);
+    cp_async_commit();
+
+    // ---- g, p of this thread's RTH x CT elements: requested now, consumed after the reconstruction ----
+    // row ga = i1 * nn + o1 -> source row i1 * mm + i2, column o1 * nn + o2 (zero outside (M, N))
+    const int ga_first = a0 + ty * RTH;
+    int i1 = ga_first / nn, o1 = ga_first - i1 * nn;
+    // 32-bit element offsets (the launcher guarantees (M + 1) * N < 2^31).  vecbits: row a is one aligned vector inside
+    // (M, N); okbits: element (a, c) of a non-vector row is inside (M, N).  Column c >= cut sits in the next i2 block:
+    // one source row down, nn columns to the left (+ hop elements).
+    int eoff[RTH];
+    uint32_t vecbits = 0, okbits = 0;
+    Raw graw[RTH], praw[RTH];
+    const int hop = N - nn;
+#pragma unroll
+    for (int a = 0; a < RTH; ++a) {
+      const bool row_ok = ga_first + a < P;
+      const int row = i1 * mm + ci2, col = o1 * nn + co2;
+      eoff[a] = row * N + col;
+      if (vec_base && row_ok && row < M && col + CT <= N && (eoff[a] % CT) == 0) {
+        vecbits |= 1u << a;
+        graw[a] = *reinterpret_cast<const Raw*>(g + eoff[a]);
+        praw[a] = *reinterpret_cast<const Raw*>(p + eoff[a]);
+      } else {
+        // unaligned / boundary rows: element loads, packed like the vector (zeros outside)
+        T tg[CT], tp[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          const int over = c >= cut ? 1 : 0;
+          const bool ok = row_ok && c < ncols && row + over < M && col + c - over * nn < N;
+          const int e = eoff[a] + c + over * hop;
+          okbits |= (ok ? 1u : 0u) << (a * CT + c);
+          tg[c] = ok ? g[e] : T(0.f);
+          tp[c] = ok ? p[e] : T(0.f);
+        }
+        memcpy(&graw[a], tg, sizeof(Raw));
+        memcpy(&praw[a], tp, sizeof(Raw));
+      }
+      if (++o1 == nn) o1 = 0, ++i1;
+    }
+
+    cp_async_wait<1>();     // this tile's stage group has landed (the next tile's may still be in flight)
+    __syncthreads();
+
+    // ---- reconstruct the old moments of the micro-tile ----
+    float am[RTH][CT], av[RTH][CT];
+#pragma unroll
+    for (int a = 0; a < RTH; ++a)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) am[a][c] = av[a][c] = 0.f;
+    if (!first_step) {
+      const float* s1m = buf + (ty * RTH) * R;
+      const float* s1v = buf + kArr + (ty * RTH) * R;
+#pragma unroll
+      for (int k0 = 0; k0 < R; k0 += KS) {
+        float x2m[KS][CT], x2v[KS][CT];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+          lds_ct<CT>(s2m + (k0 + j) * 64 + tx * CT, x2m[j]);
+          lds_ct<CT>(s2v + (k0 + j) * 64 + tx * CT, x2v[j]);
+        }
+#pragma unroll
+        for (int a = 0; a < RTH; ++a) {
+          float x1m[KS], x1v[KS];
+          lds_ct<KS>(s1m + a * R + k0, x1m);
+          lds_ct<KS>(s1v + a * R + k0, x1v);
+#pragma unroll
+          for (int j = 0; j < KS; ++j)
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+              am[a][c] = fmaf(x1m[j], x2m[j][c], am[a][c]);
+              av[a][c] = fmaf(x1v[j], x2v[j][c], av[a][c]);
+            }
+        }
+      }
+    }
+
+    // ---- Adam on p; am / av become the new moments m' / v' (zero outside (M, N)) ----
+    // sqrt.approx / rcp.approx (MUFU, <= 2 ulp each) instead of the IEEE sequences: the update term is scaled by the
+    // step size before it meets p, far inside the 2e-5 trajectory bound (tests/test_tt_gpu.py)
+    auto adam1 = [&](float& m_io, float& v_io, float gval, float& pval) {
+      const float mo = fmaf(beta1, m_io, omb1 * gval);                         // ttadam.py:92
+      const float vo = fmaf(beta2, fmaxf(v_io, 0.f), omb2 * gval * gval);      // ttadam.py:84,93
+      float sq, rc;
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(vo));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(sq + eps));
+      pval = fmaf(-step_size, mo * rc, pval);                                  // ttadam.py:94,103,108
+      pval = fmaf(-lr_wd, pval, pval);                                         // ttadam.py:110-111 (lr_wd = 0: no-op)
+      m_io = mo, v_io = vo;
+    };
+    if (vecbits == (1u << RTH) - 1u) {        // the common case: every row of the micro-tile is one aligned vector
+#pragma unroll
+      for (int a = 0; a < RTH; ++a) {
+        float gv[CT], pv[CT];
+        raw_unpack<T, CT>(graw[a], gv);
+        raw_unpack<T, CT>(praw[a], pv);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) adam1(am[a][c], av[a][c], gv[c], pv[c]);
+        *reinterpret_cast<Raw*>(p + eoff[a]) = raw_pack<T, CT>(pv);
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < RTH; ++a) {
+        float gv[CT], pv[CT];
+        raw_unpack<T, CT>(graw[a], gv);
+        raw_unpack<T, CT>(praw[a], pv);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) adam1(am[a][c], av[a][c], gv[c], pv[c]);
+        if ((vecbits >> a) & 1u) {
+          *reinterpret_cast<Raw*>(p + eoff[a]) = raw_pack<T, CT>(pv);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CT; ++c) {
+            if ((okbits >> (a * CT + c)) & 1u) store_from_f32<T>(p, eoff[a] + c + (c >= cut ? hop : 0), pv[c]);
+            else am[a][c] = av[a][c] = 0.f;
+          }
+        }
+      }
+    }
+
+    // ---- projection: acc[k][c] += Q'[row a, k] . m'[a][c] ----
+    {
+      const float* sQm = buf + 2 * kArr + (ty * RTH) * R;
+      const float* sQv = buf + 3 * kArr + (ty * RTH) * R;
+#pragma unroll
+      for (int a = 0; a < RTH; ++a)
+#pragma unroll
+        for (int k4 = 0; k4 < R / 4; ++k4) {
+          const float4 qm = *reinterpret_cast<const float4*>(sQm + a * R + 4 * k4);
+          const float4 qv = *reinterpret_cast<const float4*>(sQv + a * R + 4 * k4);
+          const float qms[4] = {qm.x, qm.y, qm.z, qm.w}, qvs[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+              accm[4 * k4 + j][c] = fmaf(qms[j], am[a][c], accm[4 * k4 + j][c]);
+              accv[4 * k4 + j][c] = fmaf(qvs[j], av[a][c], accv[4 * k4 + j][c]);
+            }
+        }
+    }
+  }
+
+  // ---- sum the TY row groups of every column (fixed order) and store this row range's partial of R' ----
+  cp_async_wait<0>();
+  float* red = fs;                  // [TY][R][64] floats = 32 KB, over the (dead) staging area
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (pass == 0) sts_ct<CT>(red + (ty * R + k) * 64 + tx * CT, accm[k]);
+      else sts_ct<CT>(red + (ty * R + k) * 64 + tx * CT, accv[k]);
+    }
+    __syncthreads();
+    float* dst = (pass == 0 ? Rm : Rv) + blockIdx.y * split_stride;
+#pragma unroll
+    for (int u = 0; u < R * 64 / 256; ++u) {
+      const int o = tid + u * 256;
+      const int k = o / 64, col = o % 64;
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < TY; ++y) s += red[(y * R + k) * 64 + col];
+      if (k < r && b0 + col < P) dst[static_cast<int64_t>(k) * P + b0 + col] = s;
     }
   }
 }
@@ -1167,29 +1580,69 @@ template <typename T, int R>
 static int launch_adam2(bool head, void* p, const void* g, const float* G1m, const float* G2m, const float* G1v,
                         const float* G2v, int r, const float* Qm, const float* Qv, float* Rm, float* Rv, float* Xm,
                         float* Xv, int M, int N, int mm, int nn, float beta1, float omb1, float beta2, float omb2, float eps,
-                        float step_size, float lr_wd, int first_step, cudaStream_t stream) {
+                        float step_size, float lr_wd, int first_step, float* part, size_t part_bytes, cudaStream_t stream) {
   const int P = mm * nn;
   const int n_tiles = ceil_div(P, 64);
   const size_t smem = (size_t(4) * R * 64 + size_t(2) * 64 * R + (R == 64 ? 0 : size_t(2) * 64 * 64)) * sizeof(float);
   if (head) {
     auto k = tt_adam2_kernel<T, R, true>;
-    SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k<<<n_tiles, 256, smem, stream>>>(static_cast<T*>(p), static_cast<const T*>(g), G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, Xm,
-                                      Xv, M, N, mm, nn, beta1, omb1, beta2, omb2, eps, step_size, lr_wd, first_step, 1);
+    SOWB_CHECK_CUDA(set_max_smem_once(k, size_t(smem)));
+    SOWB_CHECK_CUDA(launch_pdl(k, dim3(n_tiles), dim3(256), smem, stream, static_cast<T*>(p), static_cast<const T*>(g), G1m, G2m,
+                               G1v, G2v, r, Qm, Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1, beta2, omb2, eps, step_size,
+                               lr_wd, first_step, 1, int64_t(0)));
   } else {
+    if constexpr (R <= 16) {
+      // ranks <= 16: projection accumulated in registers (tt_adam2_reg_kernel); SOWB_TT_REG=0 keeps the kernel below
+      static const bool use_reg = [] { const char* e = getenv("SOWB_TT_REG"); return e == nullptr || atoi(e) != 0; }();
+      if (use_reg && nn >= 4 && (int64_t(mm) * mm + 1) * N < (int64_t(1) << 31)) {
+        constexpr int CT = 32 / R;
+        const int n_rt = ceil_div(P, kRegTileRows);
+        int splits = std::max(1, (2 * 2 * num_sms()) / n_tiles);     // two resident CTAs per SM, two waves
+        splits = std::min(splits, n_rt);
+        const int per = ceil_div(n_rt, splits);
+        splits = ceil_div(n_rt, per);
+        const int64_t rp = int64_t(r) * P;
+        float* dm = Rm;
+        float* dv = Rv;
+        if (splits > 1) {
+          const size_t need = size_t(2) * splits * rp * sizeof(float);
+          if (part == nullptr || part_bytes < need)
+            return set_error(SOWB_EWORKSPACE, "tt_adam2: workspace %zu B < %zu B for the projection partials", part_bytes, need);
+          dm = part, dv = part + splits * rp;
+        }
+        auto k = tt_adam2_reg_kernel<T, R, CT>;
+        constexpr size_t rsmem = reg_kernel_smem(R);
+        SOWB_CHECK_CUDA(set_max_smem_once(k, size_t(rsmem)));
+        SOWB_CHECK_CUDA(launch_pdl(k, dim3(n_tiles, splits), dim3(256), rsmem, stream, static_cast<T*>(p),
+                                   static_cast<const T*>(g), G1m, G2m, G1v, G2v, r, Qm, Qv, dm, dv, M, N, mm, nn, beta1, omb1,
+                                   beta2, omb2, eps, step_size, lr_wd, first_step, per, splits > 1 ? rp : int64_t(0)));
+        if (splits > 1) return launch_sum_splits(part, splits, rp, splits * rp, Rm, Rv - Rm, rp, 2, stream);
+        return SOWB_OK;
+      }
+    }
     // strips x row-ranges: enough CTAs that every SM holds as many as its shared memory admits (the per-tile chain
-    // load -> reconstruct -> update -> project is latency-bound inside one CTA); every CTA red.adds its [r x 64]
-    // accumulators once
+    // load -> reconstruct -> update -> project is latency-bound inside one CTA); every CTA stores its [r x 64]
+    // accumulators once, as the partial of its row-range, and sum_splits_kernel adds the partials in range order
     const int ctas_per_sm = std::max(1, std::min(R <= 16 ? 4 : (R <= 32 ? 3 : 2), int(size_t(220) * 1024 / smem)));
     int splits = std::max(1, (2 * ctas_per_sm * num_sms()) / n_tiles);
     splits = std::min(splits, n_tiles);
     const int per = ceil_div(n_tiles, splits);
     splits = ceil_div(n_tiles, per);
+    const int64_t rp = int64_t(r) * P;
+    float* dm = Rm;
+    float* dv = Rv;
+    if (splits > 1) {
+      const size_t need = size_t(2) * splits * rp * sizeof(float);
+      if (part == nullptr || part_bytes < need)
+        return set_error(SOWB_EWORKSPACE, "tt_adam2: workspace %zu B < %zu B for the projection partials", part_bytes, need);
+      dm = part, dv = part + splits * rp;
+    }
     auto k = tt_adam2_kernel<T, R, false>;
-    SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k<<<dim3(n_tiles, splits), 256, smem, stream>>>(static_cast<T*>(p), static_cast<const T*>(g), G1m, G2m, G1v, G2v, r, Qm,
-                                                    Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1, beta2, omb2, eps,
-                                                    step_size, lr_wd, first_step, per);
+    SOWB_CHECK_CUDA(set_max_smem_once(k, size_t(smem)));
+    SOWB_CHECK_CUDA(launch_pdl(k, dim3(n_tiles, splits), dim3(256), smem, stream, static_cast<T*>(p), static_cast<const T*>(g),
+                               G1m, G2m, G1v, G2v, r, Qm, Qv, dm, dv, Xm, Xv, M, N, mm, nn, beta1, omb1, beta2, omb2, eps,
+                               step_size, lr_wd, first_step, per, splits > 1 ? rp : int64_t(0)));
+    if (splits > 1) return launch_sum_splits(part, splits, rp, splits * rp, Rm, Rv - Rm, rp, 2, stream);
   }
   SOWB_CHECK_CUDA(cudaGetLastError());
   return SOWB_OK;
@@ -1199,10 +1652,11 @@ template <typename T>
 static int dispatch_adam2(bool head, void* p, const void* g, const float* G1m, const float* G2m, const float* G1v,
                           const float* G2v, int r, const float* Qm, const float* Qv, float* Rm, float* Rv, float* Xm,
                           float* Xv, int M, int N, int mm, int nn, float beta1, float omb1, float beta2, float omb2,
-                          float eps, float step_size, float lr_wd, int first_step, cudaStream_t stream) {
+                          float eps, float step_size, float lr_wd, int first_step, float* part, size_t part_bytes,
+                          cudaStream_t stream) {
 #define SOWB_ADAM2(RR)                                                                                                \
   return launch_adam2<T, RR>(head, p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1,     \
-                             beta2, omb2, eps, step_size, lr_wd, first_step, stream)
+                             beta2, omb2, eps, step_size, lr_wd, first_step, part, part_bytes, stream)
   if (r <= 8) SOWB_ADAM2(8);
   if (r <= 16) SOWB_ADAM2(16);
   if (r <= 32) SOWB_ADAM2(32);
@@ -1219,7 +1673,9 @@ extern "C" {
 static int adam2_common(bool head, void* p, const void* g, const float* G1m, const float* G2m, const float* G1v,
                         const float* G2v, int r, const float* Qm, const float* Qv, float* Rm, float* Rv, float* Xm,
                         float* Xv, int M, int N, int mm, int nn, double beta1_d, double beta2_d, double eps_d,
-                        double step_size_d, double lr_wd_d, int first_step, int dtype, void* stream_) {
+                        double step_size_d, double lr_wd_d, int first_step, int dtype, void* ws, size_t ws_bytes,
+                        void* stream_) {
+  float* part = static_cast<float*>(ws);
   const float beta1 = float(beta1_d), beta2 = float(beta2_d), omb1 = float(1.0 - beta1_d), omb2 = float(1.0 - beta2_d);
   SOWB_REQUIRE(g != nullptr, "tt_adam2: null gradient pointer");
   if (int rc0 = ensure_context_for(g)) return rc0;
@@ -1229,10 +1685,11 @@ static int adam2_common(bool head, void* p, const void* g, const float* G1m, con
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (dtype == SOWB_BF16)
     return dispatch_adam2<__nv_bfloat16>(head, p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1,
-                                         beta2, omb2, float(eps_d), float(step_size_d), float(lr_wd_d), first_step, stream);
+                                         beta2, omb2, float(eps_d), float(step_size_d), float(lr_wd_d), first_step, part, ws_bytes,
+                                         stream);
   if (dtype == SOWB_F32)
     return dispatch_adam2<float>(head, p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, Xm, Xv, M, N, mm, nn, beta1, omb1, beta2,
-                                 omb2, float(eps_d), float(step_size_d), float(lr_wd_d), first_step, stream);
+                                 omb2, float(eps_d), float(step_size_d), float(lr_wd_d), first_step, part, ws_bytes, stream);
   return set_error(SOWB_EINVAL, "tt_adam2: unknown dtype %d", dtype);
 }
 
@@ -1241,15 +1698,51 @@ int tt_adam2_head(const void* g, const float* G1m, const float* G2m, const float
                   void* stream) {
   SOWB_REQUIRE(Xm && Xv, "tt_adam2_head: null output pointer");
   return adam2_common(true, nullptr, g, G1m, G2m, G1v, G2v, r, nullptr, nullptr, nullptr, nullptr, Xm, Xv, M, N, mm, nn,
-                      beta1, beta2, 0.0, 0.0, 0.0, first_step, dtype, stream);
+                      beta1, beta2, 0.0, 0.0, 0.0, first_step, dtype, nullptr, 0, stream);
 }
 
 int tt_adam2_fused(void* p, const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r,
                    const float* Qm, const float* Qv, float* Rm, float* Rv, int M, int N, int mm, int nn, double beta1,
-                   double beta2, double eps, double step_size, double lr_wd, int first_step, int dtype, void* stream) {
+                   double beta2, double eps, double step_size, double lr_wd, int first_step, int dtype, void* ws,
+                   size_t ws_bytes, void* stream) {
   SOWB_REQUIRE(p && Qm && Qv && Rm && Rv, "tt_adam2_fused: null pointer argument");
   return adam2_common(false, p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, nullptr, nullptr, M, N, mm, nn, beta1, beta2, eps,
-                      step_size, lr_wd, first_step, dtype, stream);
+                      step_size, lr_wd, first_step, dtype, ws, ws_bytes, stream);
+}
+
+// upper bound of the split-partial scratch of tt_adam2_fused / tt_adam2_step: 2 moments x splits x r x P floats with
+// splits * P <= max(P, 2 * ctas_per_sm * sms * 64) and r * ctas_per_sm <= 128 on the CUDA-core kernel (launch_adam2), and
+// splits * P <= sms * 128 at r <= 64 on the tensor-core kernel (tt_tc.cu)
+size_t tt_adam2_fused_workspace_bytes(int mm, int nn) {
+  const size_t P_pad = (size_t(mm) * nn + 127) / 128 * 128;
+  const size_t elems = std::max<size_t>(size_t(64) * P_pad, size_t(128) * 2 * size_t(num_sms()) * 64);
+  return 2 * elems * sizeof(float);
+}
+
+// Cholesky-QR scratch: [2 blocks of batch x (L 64x64 + dinv 64) fp64][batch flags][Gram partials batch x n_part x r x r fp64]
+struct CqPlan {
+  bool ok;            // Cholesky-QR applies (r <= 64, m >= 64)
+  int n_part;         // Gram partials (row-block groups) per matrix
+  size_t g_bytes, flag_off, part_off, total;
+};
+
+static CqPlan cq_plan(int m, int r, int batch) {
+  CqPlan pl{};
+  pl.ok = r <= kCqMaxR && m >= 64 && batch <= 65535;
+  if (!pl.ok) return pl;
+  // enough CTAs for about two waves, never more than the 128-row blocks of one matrix
+  pl.n_part = std::max(1, std::min(ceil_div(m, kCqRows), ceil_div(2 * num_sms(), batch)));
+  pl.g_bytes = size_t(batch) * kCqWsPerBatch;
+  pl.flag_off = (2 * pl.g_bytes + 15) & ~size_t(15);
+  pl.part_off = (pl.flag_off + size_t(batch) * sizeof(int) + 15) & ~size_t(15);
+  pl.total = pl.part_off + size_t(batch) * pl.n_part * r * r * sizeof(double);
+  return pl;
+}
+
+size_t sow_thin_qr_workspace_bytes(int m, int r, int batch) {
+  if (m <= 0 || r <= 0 || batch <= 0) return 0;
+  const CqPlan pl = cq_plan(m, r, batch);
+  return pl.ok ? pl.total : size_t(batch) * m * r * sizeof(float);
 }
 
 int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64_t q_batch_stride, int m, int r,
@@ -1259,71 +1752,110 @@ int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64
   SOWB_REQUIRE(m > 0 && r > 0 && batch > 0 && ldx >= r, "sow_thin_qr: bad dimensions (m=%d r=%d ldx=%d batch=%d)", m, r, ldx, batch);
   SOWB_REQUIRE(r <= m, "sow_thin_qr: rank %d exceeds the row count %d (the reference fails here too: tt.py:135)", r, m);
   SOWB_REQUIRE(r <= 4096, "sow_thin_qr: rank %d too large", r);
+  SOWB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "sow_thin_qr: workspace must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t need = size_t(batch) * m * r * sizeof(float);
-  if (ws_bytes < need) return set_error(SOWB_EWORKSPACE, "sow_thin_qr: workspace %zu B < required %zu B", ws_bytes, need);
-  if (r <= kCqMaxR && m >= 64 && ws_bytes >= size_t(batch) * kCqWsPerBatch && batch <= 65535 &&
-      (reinterpret_cast<uintptr_t>(ws) & 7) == 0) {
-    // Cholesky-QR: Gram (all SMs) -> Cholesky (one CTA per matrix) -> triangular solve per row (all SMs)
-    double* wsd = static_cast<double*>(ws);
-    const size_t g_bytes = size_t(batch) * kCqWsPerBatch;
-    // second-pass Gram block and the per-matrix flags sit behind the first block when the workspace has room for them
-    const size_t flag_off = (2 * g_bytes + 15) & ~size_t(15);
-    const bool qr2 = ws_bytes >= flag_off + size_t(batch) * sizeof(int);
-    double* wsd2 = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + g_bytes);
-    int* flags = qr2 ? reinterpret_cast<int*>(static_cast<uint8_t*>(ws) + flag_off) : nullptr;
-    SOWB_CHECK_CUDA(cudaMemsetAsync(wsd, 0, qr2 ? 2 * g_bytes : g_bytes, stream));
+  const size_t need = sow_thin_qr_workspace_bytes(m, r, batch);
+  if (ws_bytes < need)
+    return set_error(SOWB_EWORKSPACE, "sow_thin_qr: workspace %zu B < required %zu B (sow_thin_qr_workspace_bytes)", ws_bytes, need);
+  const CqPlan pl = cq_plan(m, r, batch);
+  if (pl.ok) {
+    // Cholesky-QR: Gram partials (all SMs) -> fixed-order sum -> Cholesky (one CTA per matrix) -> triangular solve per
+    // row (all SMs)
+    uint8_t* w8 = static_cast<uint8_t*>(ws);
+    double* wsd = reinterpret_cast<double*>(w8);
+    double* wsd2 = reinterpret_cast<double*>(w8 + pl.g_bytes);          // second-pass factor block
+    int* flags = reinterpret_cast<int*>(w8 + pl.flag_off);
+    double* part = reinterpret_cast<double*>(w8 + pl.part_off);
+    dim3 ggrid(pl.n_part, batch);
     dim3 grid(ceil_div(m, kCqRows), batch);
     constexpr size_t solve_smem = (kCqMaxR * (kCqMaxR + 1) + kCqMaxR) * sizeof(double) + size_t(kCqRows) * (kCqMaxR + 1) * sizeof(float);
-    SOWB_CHECK_CUDA(cudaFuncSetAttribute(cq_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(solve_smem)));
-    cq_gram_kernel<<<grid, 256, 0, stream>>>(X, x_batch_stride, ldx, wsd, m, r, nullptr);
+    auto solve = [&](const float* src, int64_t bs, int ld, const double* fac, const int* only_if) -> cudaError_t {
+#define SOWB_CQ_SOLVE(RQ)                                                                                               \
+  do {                                                                                                                  \
+    cudaError_t e_ = set_max_smem_once(cq_solve_kernel<RQ>, solve_smem);                                                \
+    if (e_ != cudaSuccess) return e_;                                                                                   \
+    return launch_pdl(cq_solve_kernel<RQ>, grid, dim3(kCqRows), solve_smem, stream, src, bs, ld, Q, q_batch_stride,     \
+                      fac, m, r, only_if);                                                                              \
+  } while (0)
+      if (r <= 8) SOWB_CQ_SOLVE(8);
+      if (r <= 16) SOWB_CQ_SOLVE(16);
+      if (r <= 32) SOWB_CQ_SOLVE(32);
+      SOWB_CQ_SOLVE(64);
+#undef SOWB_CQ_SOLVE
+    };
+    auto gram = [&](const float* src, int64_t bs, int ld, const int* only_if) -> cudaError_t {
+      switch (ceil_div(r, 16)) {
+        case 1: return launch_pdl(cq_gram_kernel<1>, ggrid, dim3(256), 0, stream, src, bs, ld, part, m, r, only_if);
+        case 2: return launch_pdl(cq_gram_kernel<2>, ggrid, dim3(256), 0, stream, src, bs, ld, part, m, r, only_if);
+        case 3: return launch_pdl(cq_gram_kernel<3>, ggrid, dim3(256), 0, stream, src, bs, ld, part, m, r, only_if);
+        default: return launch_pdl(cq_gram_kernel<4>, ggrid, dim3(256), 0, stream, src, bs, ld, part, m, r, only_if);
+      }
+    };
+    SOWB_CHECK_CUDA(gram(X, x_batch_stride, ldx, nullptr));
     SOWB_CHECK_CUDA(cudaGetLastError());
-    cq_chol_kernel<<<batch, 1024, 0, stream>>>(wsd, r, flags, nullptr);
+    dim3 sgrid(ceil_div(r * r, 256), batch);
+    // r <= 32: the Cholesky CTA sums the partials itself (same order as cq_sum_kernel); above, the sum needs more CTAs
+    const bool fuse_sum = r <= 32;
+    const double* no_part = nullptr;
+    if (!fuse_sum) SOWB_CHECK_CUDA(launch_pdl(cq_sum_kernel, sgrid, dim3(256), 0, stream, part, pl.n_part, r, wsd, nullptr));
+    SOWB_CHECK_CUDA(launch_pdl(cq_chol_kernel, dim3(batch), dim3(1024), 0, stream, wsd, fuse_sum ? part : no_part, pl.n_part, r,
+                               flags, nullptr));
+    SOWB_CHECK_CUDA(solve(X, x_batch_stride, ldx, wsd, nullptr));
+    // CholeskyQR2 for the flagged matrices only: Q <- Q . chol(Q^T Q)^-T, in place
+    SOWB_CHECK_CUDA(gram(Q, q_batch_stride, r, flags));
     SOWB_CHECK_CUDA(cudaGetLastError());
-    cq_solve_kernel<<<grid, kCqRows, solve_smem, stream>>>(X, x_batch_stride, ldx, Q, q_batch_stride, wsd, m, r, nullptr);
-    SOWB_CHECK_CUDA(cudaGetLastError());
-    if (qr2) {
-      // CholeskyQR2 for the flagged matrices only: Q <- Q . chol(Q^T Q)^-T, in place
-      cq_gram_kernel<<<grid, 256, 0, stream>>>(Q, q_batch_stride, r, wsd2, m, r, flags);
-      SOWB_CHECK_CUDA(cudaGetLastError());
-      cq_chol_kernel<<<batch, 1024, 0, stream>>>(wsd2, r, nullptr, flags);
-      SOWB_CHECK_CUDA(cudaGetLastError());
-      cq_solve_kernel<<<grid, kCqRows, solve_smem, stream>>>(Q, q_batch_stride, r, Q, q_batch_stride, wsd2, m, r, flags);
-      SOWB_CHECK_CUDA(cudaGetLastError());
-    }
+    if (!fuse_sum) SOWB_CHECK_CUDA(launch_pdl(cq_sum_kernel, sgrid, dim3(256), 0, stream, part, pl.n_part, r, wsd2, flags));
+    SOWB_CHECK_CUDA(launch_pdl(cq_chol_kernel, dim3(batch), dim3(1024), 0, stream, wsd2, fuse_sum ? part : no_part, pl.n_part, r,
+                               nullptr, flags));
+    SOWB_CHECK_CUDA(solve(Q, q_batch_stride, r, wsd2, flags));
     return SOWB_OK;
   }
   const size_t smem = (size_t(r) + kQrWarps * 64 + size_t(kQrWarps) * 32 * 33) * sizeof(float);
-  SOWB_CHECK_CUDA(cudaFuncSetAttribute(thin_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  SOWB_CHECK_CUDA(set_max_smem_once(thin_qr_kernel, size_t(smem)));
   thin_qr_kernel<<<batch, kQrThreads, smem, stream>>>(X, x_batch_stride, ldx, Q, q_batch_stride, static_cast<float*>(ws), m, r);
   SOWB_CHECK_CUDA(cudaGetLastError());
   return SOWB_OK;
 }
 
+// row-range splits of a projection over m rows: enough CTAs for two waves, at least 4 smem stages per split
+static int project_splits(int m, int n_tiles, int batch, int* m_per) {
+  int splits = std::max(1, (2 * num_sms()) / std::max(1, n_tiles * batch));
+  splits = std::min(splits, ceil_div(m, 4 * kPjTM));
+  splits = std::max(1, std::min(splits, 65535));
+  *m_per = round_up(ceil_div(m, splits), kPjTM);
+  return ceil_div(m, *m_per);
+}
+
+size_t tt_project_workspace_bytes(int m, int n, int r, int batch) {
+  if (m <= 0 || n <= 0 || r <= 0 || batch <= 0) return 0;
+  int m_per;
+  const int splits = project_splits(m, ceil_div(n, kPjTN), batch, &m_per);
+  return splits > 1 ? size_t(batch) * splits * r * n * sizeof(float) : 0;
+}
+
 int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q_batch_stride, float* R,
-               int64_t r_batch_stride, int m, int n, int r, int batch, void* stream_) {
+               int64_t r_batch_stride, int m, int n, int r, int batch, void* ws, size_t ws_bytes, void* stream_) {
   SOWB_REQUIRE(L && Q && R, "tt_project: null pointer argument");
   if (int rc0 = ensure_context_for(L)) return rc0;
   SOWB_REQUIRE(m > 0 && n > 0 && r > 0 && batch > 0, "tt_project: bad dimensions");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int n_tiles = ceil_div(n, kPjTN);
-  int splits = std::max(1, (2 * num_sms()) / std::max(1, n_tiles * batch));
-  splits = std::min(splits, ceil_div(m, 4 * kPjTM));
-  splits = std::max(1, std::min(splits, 65535));
-  int m_per = round_up(ceil_div(m, splits), kPjTM);
-  splits = ceil_div(m, m_per);
-  if (splits > 1) {
-    if (r_batch_stride == int64_t(r) * n || batch == 1) {
-      const size_t bytes = (batch == 1) ? size_t(r) * n * 4 : size_t(batch) * r * n * 4;
-      SOWB_CHECK_CUDA(cudaMemsetAsync(R, 0, bytes, stream));
-    } else {
-      for (int b = 0; b < batch; ++b) SOWB_CHECK_CUDA(cudaMemsetAsync(R + b * r_batch_stride, 0, size_t(r) * n * 4, stream));
-    }
-  }
+  int m_per;
+  const int splits = project_splits(m, n_tiles, batch, &m_per);
+  const int64_t rn = int64_t(r) * n;
   dim3 grid(n_tiles, splits, batch);
-  tt_project_kernel<<<grid, kPjThreads, 0, stream>>>(L, l_batch_stride, Q, q_batch_stride, R, r_batch_stride, m, n, r, m_per);
+  if (splits == 1) {
+    tt_project_kernel<<<grid, kPjThreads, 0, stream>>>(L, l_batch_stride, Q, q_batch_stride, R, r_batch_stride, 0, m, n, r, m_per);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    return SOWB_OK;
+  }
+  const size_t need = size_t(batch) * splits * rn * sizeof(float);
+  if (ws == nullptr || ws_bytes < need)
+    return set_error(SOWB_EWORKSPACE, "tt_project: workspace %zu B < required %zu B (tt_project_workspace_bytes)", ws_bytes, need);
+  float* part = static_cast<float*>(ws);
+  tt_project_kernel<<<grid, kPjThreads, 0, stream>>>(L, l_batch_stride, Q, q_batch_stride, part, splits * rn, rn, m, n, r, m_per);
   SOWB_CHECK_CUDA(cudaGetLastError());
-  return SOWB_OK;
+  return launch_sum_splits(part, splits, rn, splits * rn, R, r_batch_stride, rn, batch, stream);
 }
 
 int tt_gather2(const void* src, int M, int N, int mm, int nn, float* X, int ncols, int dtype, void* stream_) {
@@ -1342,27 +1874,38 @@ int tt_gather2(const void* src, int M, int N, int mm, int nn, float* X, int ncol
   return SOWB_OK;
 }
 
-int tt_project2(const void* src, int M, int N, int mm, int nn, const float* Q, float* R, int r, int dtype, void* stream_) {
+size_t tt_project2_workspace_bytes(int mm, int nn, int r) {
+  if (mm <= 0 || nn <= 0 || r <= 0) return 0;
+  return tt_project_workspace_bytes(mm * nn, mm * nn, r, 1);
+}
+
+int tt_project2(const void* src, int M, int N, int mm, int nn, const float* Q, float* R, int r, int dtype, void* ws,
+                size_t ws_bytes, void* stream_) {
   SOWB_REQUIRE(src && Q && R, "tt_project2: null pointer argument");
   SOWB_REQUIRE(mm > 0 && nn > 0 && r > 0 && int64_t(mm) * mm >= M && int64_t(nn) * nn >= N, "tt_project2: bad shape");
+  SOWB_REQUIRE(dtype == SOWB_BF16 || dtype == SOWB_F32, "tt_project2: unknown dtype %d", dtype);
   if (int rc0 = ensure_context_for(src)) return rc0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int P = mm * nn;
   const int n_tiles = ceil_div(P, kPjTN);
-  int splits = std::max(1, (2 * num_sms()) / std::max(1, n_tiles));
-  splits = std::min(splits, ceil_div(P, 4 * kPjTM));
-  splits = std::max(1, std::min(splits, 65535));
-  const int m_per = round_up(ceil_div(P, splits), kPjTM);
-  splits = ceil_div(P, m_per);
-  if (splits > 1) SOWB_CHECK_CUDA(cudaMemsetAsync(R, 0, size_t(r) * P * 4, stream));
+  int m_per;
+  const int splits = project_splits(P, n_tiles, 1, &m_per);
+  const int64_t rp = int64_t(r) * P;
+  float* dst = R;
+  if (splits > 1) {
+    const size_t need = size_t(splits) * rp * sizeof(float);
+    if (ws == nullptr || ws_bytes < need)
+      return set_error(SOWB_EWORKSPACE, "tt_project2: workspace %zu B < required %zu B (tt_project2_workspace_bytes)", ws_bytes, need);
+    dst = static_cast<float*>(ws);
+  }
+  const int64_t stride = splits > 1 ? rp : 0;
   dim3 grid(n_tiles, splits);
   if (dtype == SOWB_BF16)
-    tt_project2_kernel<__nv_bfloat16><<<grid, kPjThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), M, N, mm, nn, Q, R, r, m_per);
-  else if (dtype == SOWB_F32)
-    tt_project2_kernel<float><<<grid, kPjThreads, 0, stream>>>(static_cast<const float*>(src), M, N, mm, nn, Q, R, r, m_per);
+    tt_project2_kernel<__nv_bfloat16><<<grid, kPjThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), M, N, mm, nn, Q, dst, stride, r, m_per);
   else
-    return set_error(SOWB_EINVAL, "tt_project2: unknown dtype %d", dtype);
+    tt_project2_kernel<float><<<grid, kPjThreads, 0, stream>>>(static_cast<const float*>(src), M, N, mm, nn, Q, dst, stride, r, m_per);
   SOWB_CHECK_CUDA(cudaGetLastError());
+  if (splits > 1) return launch_sum_splits(dst, splits, rp, 0, R, 0, rp, 1, stream);
   return SOWB_OK;
 }
 
@@ -1447,12 +1990,12 @@ int tt_adam_fused2(void* p, const void* g, const float* G1m, const float* G2m, c
   const size_t smem = size_t(4) * r * 64 * sizeof(float);
   if (dtype == SOWB_BF16) {
     auto k = tt_adam_fused2_kernel<__nv_bfloat16>;
-    SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SOWB_CHECK_CUDA(set_max_smem_once(k, size_t(smem)));
     k<<<grid, 256, smem, stream>>>(static_cast<__nv_bfloat16*>(p), static_cast<const __nv_bfloat16*>(g), G1m, G2m, G1v,
                                    G2v, r, m_out, v_out, M, N, mm, nn, beta1, omb1, beta2, omb2, eps, step_size, lr_wd, first_step);
   } else if (dtype == SOWB_F32) {
     auto k = tt_adam_fused2_kernel<float>;
-    SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SOWB_CHECK_CUDA(set_max_smem_once(k, size_t(smem)));
     k<<<grid, 256, smem, stream>>>(static_cast<float*>(p), static_cast<const float*>(g), G1m, G2m, G1v, G2v, r, m_out,
                                    v_out, M, N, mm, nn, beta1, omb1, beta2, omb2, eps, step_size, lr_wd, first_step);
   } else {

@@ -13,7 +13,8 @@
 //   3. UMMA: D_m[128 cols x 64] += m'^T . Q'm[tile rows]   (pieces of Q' loaded by TMA, accumulated over the tiles)
 //   4. epilogue B: v' recomputed from S_v and g (keeping both moments' operand tiles would not fit 227 KB), pieces,
 //      UMMA: D_v += v'^T . Q'v
-// At the end of the range D_m, D_v are red.add-ed into R'{m,v}[r, P].  The dense moments never exist in HBM.
+// At the end of the range D_m, D_v are stored as that range's partial of R'{m,v}[r, P] (summed in range order by
+// sum_splits_kernel: bit-reproducible).  The dense moments never exist in HBM.
 // This first version is phase-serial inside a CTA (one thread issues TMA and UMMAs, everybody waits on the mbarriers);
 // the next step is to overlap the phases of consecutive tiles.
 #include "common.cuh"
@@ -31,10 +32,22 @@ constexpr int kTcQBytes = 96 * 1024;     // Q'm pieces 48 KB + Q'v pieces 48 KB
 constexpr int kTcSmem = 1024 + kTcOpBytes + kTcQBytes + 128;
 constexpr uint32_t kTcTmemCols = 512;
 
-// x -> three bf16 pieces, written to dst[piece][rows_pad][cols_pad] (zero outside the source extent)
-__global__ void tt_split3_kernel(const float* __restrict__ src, int rows, int cols, int ld, __nv_bfloat16* __restrict__ dst,
-                                 int rows_pad, int cols_pad) {
-  const int64_t n = static_cast<int64_t>(rows_pad) * cols_pad;
+// x -> three bf16 pieces, written to dst[piece][rows_pad][cols_pad] (zero outside the source extent).  Up to six
+// operand arrays (old cores and new bases of both moments) in ONE launch: blockIdx.y selects the job.
+struct SplitJobs {
+  const float* src[6];
+  __nv_bfloat16* dst[6];
+  int rows[6], cols[6], ld[6], rows_pad[6], cols_pad[6];
+};
+
+__global__ void tt_split3_kernel(const __grid_constant__ SplitJobs jobs) {
+  pdl_trigger();
+  pdl_wait();
+  const int jb = blockIdx.y;
+  const float* __restrict__ src = jobs.src[jb];
+  __nv_bfloat16* __restrict__ dst = jobs.dst[jb];
+  const int rows = jobs.rows[jb], cols = jobs.cols[jb], ld = jobs.ld[jb], cols_pad = jobs.cols_pad[jb];
+  const int64_t n = static_cast<int64_t>(jobs.rows_pad[jb]) * cols_pad;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < n;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int i = static_cast<int>(idx / cols_pad), j = static_cast<int>(idx - static_cast<int64_t>(i) * cols_pad);
@@ -147,8 +160,9 @@ struct TcParams {
   int M, N, mm, nn, P, P_pad, r;
   float beta1, omb1, beta2, omb2, eps, step_size, lr_wd;
   int first_step, tiles_per_cta;
-  float* Rm;
+  float* Rm;             // results (one split) or the split partials [split][r][P] of each moment
   float* Rv;
+  int64_t split_stride;  // r * P when the row-range splits store partials, else 0
   long long* dbg;   // debug timeline (clock64 stamps of CTA (0,0), 8 per tile) or nullptr
 };
 
@@ -189,6 +203,8 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();
+  pdl_wait();       // barriers, tensor-map prefetch and the TMEM allocation overlap the predecessor's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS_m = tmem_base, tS_v = tmem_base + 128, tD_m = tmem_base + 256, tD_v = tmem_base + 320;
 
@@ -475,19 +491,19 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
     }
   }
 
-  // ---------------- R'[k, b0 + row] += D[row, k]: warps 0-3 -> moment m, warps 4-7 -> moment v ----------------
+  // ---------------- R'[k, b0 + row] (this row-range's partial) = D[row, k]: warps 0-3 -> moment m, warps 4-7 -> v ----
   if (t_begin < t_end) {
     uint32_t d0[32], d1[32];
     const uint32_t tD = (half ? tD_v : tD_m) + lane_off;
     tmem_ld32(tD, d0);
     tmem_ld32(tD + 32, d1);
     tmem_ld_wait();
-    float* R = half ? prm.Rv : prm.Rm;
+    float* R = (half ? prm.Rv : prm.Rm) + blockIdx.y * prm.split_stride;
     const int gb = b0 + rloc;
     if (gb < P) {
 #pragma unroll
       for (int k = 0; k < 64; ++k)
-        if (k < prm.r) atomicAdd(R + static_cast<int64_t>(k) * P + gb, __uint_as_float(k < 32 ? d0[k] : d1[k - 32]));
+        if (k < prm.r) R[static_cast<int64_t>(k) * P + gb] = __uint_as_float(k < 32 ? d0[k] : d1[k - 32]);
     }
   }
   tc_fence_before();
@@ -512,12 +528,19 @@ int tt_adam2_debug_timeline(void* buf) {
   return SOWB_OK;
 }
 
+// thin-QR scratch of the two (P x r) bases, sized for the largest rank (r <= 64)
+static size_t adam2_qr_bytes(size_t P) {
+  const int Pi = static_cast<int>(P);
+  return align256(std::max(sow_thin_qr_workspace_bytes(Pi, std::min(64, Pi), 2), 2 * 64 * P * sizeof(float)));
+}
+
 size_t tt_adam2_workspace_bytes(int mm, int nn) {
   const size_t P = size_t(mm) * nn, P_pad = (P + 127) / 128 * 128;
   const size_t piece_arr = 3 * P_pad * 64 * sizeof(__nv_bfloat16);      // one operand array: 3 pieces of [P_pad x 64]
   return align256(2 * P * 64 * sizeof(float))                            // X{m,v}: first 64 columns of the new moments
-         + align256(2 * (64 * 64 + 64) * sizeof(double) + 2 * 64 * P * sizeof(float))   // thin-QR scratch
-         + 6 * align256(piece_arr);
+         + adam2_qr_bytes(P)                                                    // thin-QR scratch
+         + 6 * align256(piece_arr)
+         + align256(tt_adam2_fused_workspace_bytes(mm, nn));                    // split partials of R'{m,v}
 }
 
 int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, const float* G1v, const float* G2v, int r,
@@ -542,11 +565,14 @@ int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, co
   float* X = reinterpret_cast<float*>(w);
   w += align256(2 * size_t(P) * 64 * sizeof(float));
   void* qr_ws = w;
-  const size_t qr_ws_bytes = align256(2 * (64 * 64 + 64) * sizeof(double) + 2 * 64 * size_t(P) * sizeof(float));
+  const size_t qr_ws_bytes = adam2_qr_bytes(size_t(P));
   w += qr_ws_bytes;
   const size_t piece_arr = align256(3 * size_t(P_pad) * 64 * sizeof(__nv_bfloat16));
   __nv_bfloat16* pcs[6];
   for (int i = 0; i < 6; ++i) pcs[i] = reinterpret_cast<__nv_bfloat16*>(w + i * piece_arr);
+  w += 6 * piece_arr;
+  float* part = reinterpret_cast<float*>(w);
+  const size_t part_bytes = tt_adam2_fused_workspace_bytes(mm, nn);
 
   // 1. first 64 columns of the new moments -> thin QR -> new bases Q'{m,v} (P x r)
   rc = tt_adam2_head(g, G1m, G2m, G1v, G2v, r, X, X + size_t(P) * 64, M, N, mm, nn, beta1, beta2, first_step, dtype, stream_);
@@ -558,16 +584,16 @@ int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, co
   // kernel is faster.  SOWB_TT_TC=0/1 forces one of them (tests exercise both).
   bool use_tc = r > 16 && nn % 8 == 0 && N % 8 == 0;
   if (const char* e = getenv("SOWB_TT_TC")) use_tc = atoi(e) != 0;
-  SOWB_CHECK_CUDA(cudaMemsetAsync(Rm, 0, size_t(r) * P * sizeof(float), stream));
-  SOWB_CHECK_CUDA(cudaMemsetAsync(Rv, 0, size_t(r) * P * sizeof(float), stream));
   if (!use_tc)
     return tt_adam2_fused(p, g, G1m, G2m, G1v, G2v, r, Qm, Qv, Rm, Rv, M, N, mm, nn, beta1, beta2, eps, step_size, lr_wd,
-                          first_step, dtype, stream_);
+                          first_step, dtype, part, part_bytes, stream_);
   // 2. bf16 pieces of the operands: G1 [P x r] -> [3][P_pad][64]; G2 [r x P] -> [3][64][P_pad]; Q' like G1
+  SplitJobs jobs = {};
+  int n_jobs = 0;
   auto split = [&](const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, int rows_pad, int cols_pad) {
-    const int64_t n = int64_t(rows_pad) * cols_pad;
-    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, int64_t(num_sms()) * 8));
-    tt_split3_kernel<<<blocks, 256, 0, stream>>>(src, rows, cols, ld, dst, rows_pad, cols_pad);
+    jobs.src[n_jobs] = src, jobs.dst[n_jobs] = dst, jobs.rows[n_jobs] = rows, jobs.cols[n_jobs] = cols, jobs.ld[n_jobs] = ld;
+    jobs.rows_pad[n_jobs] = rows_pad, jobs.cols_pad[n_jobs] = cols_pad;
+    ++n_jobs;
   };
   if (!first_step) {
     split(G1m, P, r, r, pcs[0], P_pad, 64);
@@ -577,7 +603,11 @@ int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, co
   }
   split(Qm, P, r, r, pcs[4], P_pad, 64);
   split(Qv, P, r, r, pcs[5], P_pad, 64);
-  SOWB_CHECK_CUDA(cudaGetLastError());
+  {
+    const int64_t n = int64_t(P_pad) * 64;      // every job has P_pad * 64 elements
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, int64_t(num_sms()) * 2));
+    SOWB_CHECK_CUDA(launch_pdl(tt_split3_kernel, dim3(blocks, n_jobs), dim3(256), 0, stream, jobs));
+  }
 
   // 3. tensor maps: row-stacked pieces.  G1 / Q': [3*P_pad rows, 64 cols], box 64 x 128; G2: [3*64 rows, P_pad cols], box 64 x 64
   CUtensorMap tmG1m, tmG1v, tmG2m, tmG2v, tmQm, tmQv;
@@ -601,28 +631,35 @@ int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, co
   prm.beta1 = float(beta1), prm.omb1 = float(1.0 - beta1), prm.beta2 = float(beta2), prm.omb2 = float(1.0 - beta2);
   prm.eps = float(eps), prm.step_size = float(step_size), prm.lr_wd = float(lr_wd);
   prm.first_step = first_step;
-  prm.Rm = Rm, prm.Rv = Rv;
   prm.dbg = g_tt_dbg;
   const int n_tiles = ceil_div(P, kTcTile);
   int splits = std::max(1, num_sms() / n_tiles);            // one CTA per SM (192 KB of shared memory each)
   splits = std::min(splits, n_tiles);
   prm.tiles_per_cta = ceil_div(n_tiles, splits);
-  splits = ceil_div(n_tiles, prm.tiles_per_cta);
+  splits = ceil_div(n_tiles, prm.tiles_per_cta);            // every row-range is non-empty: every partial is written
+  // row-range splits store partials of R'{m,v}; sum_splits_kernel adds them in range order (bit-reproducible)
+  const int64_t rp = int64_t(r) * P;
+  prm.Rm = Rm, prm.Rv = Rv, prm.split_stride = 0;
+  if (splits > 1) {
+    SOWB_REQUIRE(size_t(2) * splits * rp * sizeof(float) <= part_bytes, "tt_adam2_step: partial scratch too small");
+    prm.Rm = part, prm.Rv = part + splits * rp, prm.split_stride = rp;
+  }
   dim3 grid(n_tiles, splits);
   if (dtype == SOWB_BF16) {
     auto k = tt_adam2_tc_kernel<__nv_bfloat16>;
-    SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-    k<<<grid, kTcThreads, kTcSmem, stream>>>(tmG1m, tmG1v, tmG2m, tmG2v, tmQm, tmQv, static_cast<__nv_bfloat16*>(p),
-                                             static_cast<const __nv_bfloat16*>(g), prm);
+    SOWB_CHECK_CUDA(set_max_smem_once(k, size_t(kTcSmem)));
+    SOWB_CHECK_CUDA(launch_pdl(k, grid, dim3(kTcThreads), size_t(kTcSmem), stream, tmG1m, tmG1v, tmG2m, tmG2v, tmQm, tmQv,
+                               static_cast<__nv_bfloat16*>(p), static_cast<const __nv_bfloat16*>(g), prm));
   } else if (dtype == SOWB_F32) {
     auto k = tt_adam2_tc_kernel<float>;
-    SOWB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-    k<<<grid, kTcThreads, kTcSmem, stream>>>(tmG1m, tmG1v, tmG2m, tmG2v, tmQm, tmQv, static_cast<float*>(p),
-                                             static_cast<const float*>(g), prm);
+    SOWB_CHECK_CUDA(set_max_smem_once(k, size_t(kTcSmem)));
+    SOWB_CHECK_CUDA(launch_pdl(k, grid, dim3(kTcThreads), size_t(kTcSmem), stream, tmG1m, tmG1v, tmG2m, tmG2v, tmQm, tmQv,
+                               static_cast<float*>(p), static_cast<const float*>(g), prm));
   } else {
     return set_error(SOWB_EINVAL, "tt_adam2_step: unknown dtype %d", dtype);
   }
   SOWB_CHECK_CUDA(cudaGetLastError());
+  if (splits > 1) return launch_sum_splits(part, splits, rp, splits * rp, Rm, Rv - Rm, rp, 2, stream);
   return SOWB_OK;
 }
 

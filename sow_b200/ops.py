@@ -265,11 +265,12 @@ def thin_qr(X: torch.Tensor, r: int) -> torch.Tensor:
         Xb = Xb.contiguous()
     b, m, n = Xb.shape
     Q = torch.empty((b, m, r), dtype=torch.float32, device=X.device)
-    # scratch: column-major CGS2 work copy (b*r*m floats) or, for r <= 64, the fp64 Gram / Cholesky block per matrix
-    # (r <= 64: two Gram / Cholesky blocks per matrix -- the second one for the CholeskyQR2 pass of ill-conditioned inputs --
-    # and one flag per matrix behind them)
-    work = torch.empty((max(b * r * m, 2 * b * 8448 + b + 8),), dtype=torch.float32, device=X.device)
-    rc = lib.sow_thin_qr(_p(Xb), Xb.stride(0), Xb.stride(1), _p(Q), m * r, m, r, b, _p(work), work.numel() * 4,
+    # scratch: for r <= 64 two Cholesky blocks per matrix (the second for the CholeskyQR2 pass of ill-conditioned
+    # inputs), one flag per matrix and the fp64 Gram partials; above that the column-major Gram-Schmidt work copy
+    if r > m:
+        raise SowB200Error(f"thin_qr: rank {r} exceeds the row count {m} (the reference fails here too: tt.py:135)")
+    work = workspace(X.device, lib.sow_thin_qr_workspace_bytes(m, r, b))
+    rc = lib.sow_thin_qr(_p(Xb), Xb.stride(0), Xb.stride(1), _p(Q), m * r, m, r, b, _p(work), work.numel(),
                          _stream_ptr(X.device))
     check(rc, "sow_thin_qr")
     launch_counter["kernels"] += 1
@@ -286,7 +287,10 @@ def project(L: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
     b, m, n = Lb.shape
     r = Qb.shape[2]
     R = torch.empty((b, r, n), dtype=torch.float32, device=L.device)
-    rc = lib.tt_project(_p(Lb), m * n, _p(Qb), m * r, _p(R), r * n, m, n, r, b, _stream_ptr(L.device))
+    ws_bytes = lib.tt_project_workspace_bytes(m, n, r, b)      # split partials, summed in split order (no atomics)
+    ws = workspace(L.device, ws_bytes) if ws_bytes else None
+    rc = lib.tt_project(_p(Lb), m * n, _p(Qb), m * r, _p(R), r * n, m, n, r, b, _p(ws) if ws is not None else None,
+                        ws_bytes, _stream_ptr(L.device))
     check(rc, "tt_project")
     launch_counter["kernels"] += 2
     return R[0] if squeeze else R
@@ -331,7 +335,10 @@ def decompose2(src: torch.Tensor, mm: int, nn: int, r: int):
     check(lib.tt_gather2(_p(src), M, N, mm, nn, _p(X), ncols, dt, st), "tt_gather2")
     Q = thin_qr(X, r)
     R = torch.empty((r, P), dtype=torch.float32, device=src.device)
-    check(lib.tt_project2(_p(src), M, N, mm, nn, _p(Q), _p(R), r, dt, st), "tt_project2")
+    ws_bytes = lib.tt_project2_workspace_bytes(mm, nn, r)
+    ws = workspace(src.device, ws_bytes) if ws_bytes else None
+    check(lib.tt_project2(_p(src), M, N, mm, nn, _p(Q), _p(R), r, dt, _p(ws) if ws is not None else None, ws_bytes, st),
+          "tt_project2")
     launch_counter["kernels"] += 3
     return Q, R
 
@@ -413,6 +420,48 @@ def tt_adam2_step(p, g, cores_m, cores_v, mm, nn, r, beta1, beta2, eps, step_siz
     check(rc, "tt_adam2_step")
     launch_counter["kernels"] += 8
     return (Q[0], R[0]), (Q[1], R[1])
+
+
+class TTAdam2Plan:
+    """Persistent state of the fused order-2 TT-Adam step of ONE parameter: two sets of cores (Q (2,P,r) | R (2,r,P), one
+    for each moment) used ping-pong -- a step reads set ``cur`` and writes the other one -- with their C pointers built
+    once.  A step is then one C-ABI call and no allocation; the host cost per parameter drops from ~100 us (tensor
+    allocation, reshapes, TensorTrain construction, argument marshalling) to the ~30 us of the launches themselves,
+    which is what keeps a many-parameter TTAdam.step GPU-bound.  ``cores(k)`` are views, so a TensorTrain built on a
+    set is overwritten two steps later (the reference allocates new cores every step, ttadam.py:113-115)."""
+
+    def __init__(self, device, mm: int, nn: int, r: int):
+        lib = _lib.load()
+        self.mm, self.nn, self.r, self.P = mm, nn, r, mm * nn
+        P = self.P
+        self.Q = [torch.empty((2, P, r), dtype=torch.float32, device=device) for _ in range(2)]
+        self.R = [torch.empty((2, r, P), dtype=torch.float32, device=device) for _ in range(2)]
+        self._ptr = [[_p(self.Q[k][0]), _p(self.R[k][0]), _p(self.Q[k][1]), _p(self.R[k][1])] for k in range(2)]
+        self.ws_bytes = lib.tt_adam2_workspace_bytes(mm, nn)
+        self.device = device
+        self.cur = -1                      # set holding the current cores (-1: none yet)
+
+    def cores(self, k: int):
+        """((G1m (1,mm,nn,r), G2m (r,mm,nn,1)), (G1v, G2v)) of set k, as views."""
+        mm, nn, r = self.mm, self.nn, self.r
+        return tuple((self.Q[k][b].reshape(1, mm, nn, r), self.R[k][b].reshape(r, mm, nn, 1)) for b in range(2))
+
+    def step(self, p, g, beta1, beta2, eps, step_size, lr_wd) -> int:
+        """One update of p from g; returns the index of the core set that now holds the moments."""
+        lib = _lib.load()
+        first = self.cur < 0
+        out = 0 if first else 1 - self.cur
+        g1m, g2m, g1v, g2v = (None, None, None, None) if first else self._ptr[self.cur]
+        qm, rm, qv, rv = self._ptr[out]
+        M, N = p.shape
+        ws = workspace(self.device, self.ws_bytes)
+        rc = lib.tt_adam2_step(_p(p), _p(g), g1m, g2m, g1v, g2v, self.r, qm, qv, rm, rv, M, N, self.mm, self.nn,
+                               float(beta1), float(beta2), float(eps), float(step_size), float(lr_wd), 1 if first else 0,
+                               _dtype_code(p.dtype), _p(ws), ws.numel(), _stream_ptr(self.device))
+        check(rc, "tt_adam2_step")
+        launch_counter["kernels"] += 8
+        self.cur = out
+        return out
 
 
 def tt_adam_interleaved(p, g, m, v, mm, nn, order, beta1, beta2, eps, step_size, lr_wd):

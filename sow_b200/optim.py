@@ -58,7 +58,10 @@ class TTAdam(torch.optim.Optimizer):
                     step_size = step_size * math.sqrt(bc2) / bc1
                 lr_wd = group["lr"] * group["weight_decay"] if group["weight_decay"] > 0.0 else 0.0
                 if "ranks" in group and grad.dim() == 2:
-                    self._tt_update(p, grad, state, list(group["ranks"]), first, beta1, beta2, group["eps"], step_size, lr_wd)
+                    if not hasattr(self, "_tt2_plans"):
+                        self._tt2_plans = {}           # per-parameter plans of the fused order-2 path (not part of state_dict)
+                    self._tt_update(p, grad, state, list(group["ranks"]), first, beta1, beta2, group["eps"], step_size, lr_wd,
+                                    self._tt2_plans)
                 else:
                     self._dense_update(p, grad, state, first, beta1, beta2, group["eps"], step_size, lr_wd)
         return loss
@@ -77,7 +80,8 @@ class TTAdam(torch.optim.Optimizer):
         ops.tt_adam_dense(pd, g, state["exp_avg"], state["exp_avg_sq"], beta1, beta2, eps, step_size, lr_wd)
 
     @staticmethod
-    def _tt_update(p, grad, state, ranks, first, beta1, beta2, eps, step_size, lr_wd):
+    def _tt_update(p, grad, state, ranks, first, beta1, beta2, eps, step_size, lr_wd, plans=None):
+        plans = {} if plans is None else plans
         order = len(ranks) - 1
         M, N = grad.shape
         mm = ceil(M ** (1 / order))
@@ -92,6 +96,35 @@ class TTAdam(torch.optim.Optimizer):
         else:
             state["exp_avg_expr"] = None
             state["exp_avg_sq_expr"] = None
+        if order == 2 and ranks[1] <= 64 and ranks[1] <= mm * nn_ and g.is_contiguous():
+            # fused path, Adam + re-compression in one pass over p and g (the dense moments never reach HBM), through a
+            # per-parameter plan: persistent core buffers (ping-pong), pre-built TensorTrain views, one C-ABI call
+            plan = plans.get(p)
+            if plan is not None and first:
+                plan.cur = -1                                                   # state was reset: start from zero moments
+            live = (plan is not None and not first and plan.cur >= 0 and state["exp_avg"] is plan.tts[plan.cur][0]
+                    and state["exp_avg_sq"] is plan.tts[plan.cur][1])
+            if plan is None or (plan.mm, plan.nn, plan.r) != (mm, nn_, ranks[1]) or not (first or live):
+                plan = ops.TTAdam2Plan(pd.device, mm, nn_, ranks[1])
+                plan.tts = []
+                for k in range(2):
+                    pair = []
+                    for cores in plan.cores(k):
+                        tt = TensorTrain(list(ranks), (mm, mm), (nn_, nn_), device=pd.device)
+                        tt.cores = list(cores)
+                        pair.append(tt)
+                    plan.tts.append(pair)
+                plans[p] = plan
+                if not first:
+                    # moments that did not come from this plan (loaded checkpoint, replaced by the caller): copy them in
+                    P = mm * nn_
+                    for b, key in enumerate(("exp_avg", "exp_avg_sq")):
+                        plan.Q[0][b].copy_(state[key].cores[0].reshape(P, -1))
+                        plan.R[0][b].copy_(state[key].cores[1].reshape(-1, P))
+                    plan.cur = 0
+            k = plan.step(pd, g, beta1, beta2, eps, step_size, lr_wd)
+            state["exp_avg"], state["exp_avg_sq"] = plan.tts[k]
+            return
         if order == 2:
             r = ranks[1]
             P = mm * nn_

@@ -17,8 +17,8 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     names = declared_symbols()
-    for must in ["sow_group_fwd", "sow_group_bwd", "sow_group_workspace_bytes", "sow_merge_grouped", "sow_thin_qr",
-                 "tt_project", "tt_interleave", "tt_deinterleave", "tt_matmul_rk", "tt_gather2", "tt_project2", "tt_reconstruct2", "tt_adam_fused2", "tt_adam2_head", "tt_adam2_fused", "tt_adam2_workspace_bytes", "tt_adam2_step", "tt_adam_interleaved", "tt_adam_dense",
+    for must in ["sow_group_fwd", "sow_group_bwd", "sow_group_workspace_bytes", "sow_merge_grouped", "sow_thin_qr", "sow_thin_qr_workspace_bytes",
+                 "tt_project", "tt_project_workspace_bytes", "tt_project2_workspace_bytes", "tt_adam2_fused_workspace_bytes", "tt_interleave", "tt_deinterleave", "tt_matmul_rk", "tt_gather2", "tt_project2", "tt_reconstruct2", "tt_adam_fused2", "tt_adam2_head", "tt_adam2_fused", "tt_adam2_workspace_bytes", "tt_adam2_step", "tt_adam_interleaved", "tt_adam_dense",
                  "sow_adam_multi", "sow_last_error", "sow_abi_version"]:
         assert must in names, must
 
@@ -35,7 +35,7 @@ def test_ctypes_signatures_cover_the_header():
     from sow_b200 import _lib
     assert sorted(_lib.SIGNATURES.keys()) == declared_symbols()
     lib = _lib.load()
-    assert lib.sow_abi_version() == 2
+    assert lib.sow_abi_version() == 3
     assert lib.sow_rank_pad(50) == 64 and lib.sow_rank_pad(8) == 64 and lib.sow_rank_pad(65) == 128
     gm = (_lib.GroupMember * 1)()
     gm[0].out_features, gm[0].r, gm[0].scale = 2736, 50, 1.0

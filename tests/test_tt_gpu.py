@@ -166,3 +166,85 @@ def test_projection_matches_oracle_at_4096(golden_tt):
     assert rel_err(back, back_o) < 1e-5
     e, eo = rel_err(back, ema), rel_err(back_o, ema)
     assert abs(e - eo) <= 1e-5 * eo
+
+
+@pytest.mark.parametrize("r,force_tc", [(8, "0"), (32, "1"), (64, "1"), (48, "0")])
+def test_ttadam_step_is_bit_reproducible(r, force_tc, monkeypatch):
+    """Every cross-CTA sum on the TT path is a fixed-order sum of split partials (Gram of the thin QR, the projections,
+    the R' accumulation of both fused TT-Adam kernels): the same inputs give the same bits, run after run."""
+    from sow_b200 import ops
+    monkeypatch.setenv("SOWB_TT_TC", force_tc)
+    M = N = 1024
+    mm = nn_ = 32
+    torch.manual_seed(3)
+    p0 = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    g = (0.01 * torch.randn(M, N, device="cuda")).to(torch.bfloat16)
+    outs = []
+    for _ in range(3):
+        p = p0.clone()
+        (Qm, Rm), (Qv, Rv) = ops.tt_adam2_step(p, g, None, None, mm, nn_, r, 0.9, 0.999, 1e-8, 1e-3, 0.0, True)
+        cm, cv = (Qm.clone(), Rm.clone()), (Qv.clone(), Rv.clone())
+        (Qm2, Rm2), (Qv2, Rv2) = ops.tt_adam2_step(p, g, cm, cv, mm, nn_, r, 0.9, 0.999, 1e-8, 1e-3, 0.0, False)
+        outs.append([t.clone() for t in (p, Qm, Rm, Qv, Rv, Qm2, Rm2, Qv2, Rv2)])
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
+
+
+def test_decompose_is_bit_reproducible():
+    from sow_b200 import ops
+    torch.manual_seed(4)
+    mat = torch.randn(4096, 4096, device="cuda")
+    ref = None
+    for _ in range(3):
+        Q, R = ops.decompose2(mat, 64, 64, 16)
+        L = torch.randn(2, 4096, 512, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+        Qb = ops.thin_qr(L, 24)
+        Rb = ops.project(L, Qb)
+        cur = [Q.clone(), R.clone(), Qb.clone(), Rb.clone()]
+        if ref is None:
+            ref = cur
+        for a, b in zip(ref, cur):
+            assert torch.equal(a, b)
+
+
+def test_ttadam_plan_survives_replaced_and_reset_state(golden_tt):
+    """The fused order-2 path keeps persistent core buffers per parameter.  Moments that were replaced behind its back (a
+    loaded checkpoint) must be picked up, and a cleared state must restart from zero moments: both runs reproduce the
+    uninterrupted trajectory bit for bit."""
+    from tn_gradient.optimizer.ttadam import TTAdam
+    from tn_gradient.tt import TensorTrain
+    g = golden_tt
+    grads = [torch.from_numpy(x).cuda() for x in g["ttadam/o2/grads"]]
+    ranks = [int(r) for r in g["ttadam/o2/ranks"]]
+
+    def run(interfere):
+        p = torch.nn.Parameter(torch.from_numpy(g["ttadam/o2/p0"]).cuda())
+        opt = TTAdam([{"params": [p], "ranks": list(ranks)}], lr=1e-2)
+        for step, grad in enumerate(grads):
+            p.grad = grad
+            opt.step()
+            if interfere and step == 1:
+                st = opt.state[p]
+                for key in ("exp_avg", "exp_avg_sq"):                 # what load_state_dict leaves behind
+                    st[key] = TensorTrain.from_cores([c.clone() for c in st[key].cores])
+        return p.detach().clone(), [c.clone() for c in opt.state[p]["exp_avg"].cores]
+
+    p_ref, cores_ref = run(False)
+    p_int, cores_int = run(True)
+    assert torch.equal(p_ref, p_int)
+    for a, b in zip(cores_ref, cores_int):
+        assert torch.equal(a, b)
+    assert rel_err(p_ref.cpu().numpy(), g["ttadam/o2/p5"]) < 2e-5
+
+    # reset: clearing the state restarts from zero moments (the plan's stale cores must not leak in)
+    p = torch.nn.Parameter(torch.from_numpy(g["ttadam/o2/p0"]).cuda())
+    opt = TTAdam([{"params": [p], "ranks": list(ranks)}], lr=1e-2)
+    p.grad = grads[0]
+    opt.step()
+    p1 = p.detach().clone()
+    opt.state[p].clear()
+    with torch.no_grad():
+        p.copy_(torch.from_numpy(g["ttadam/o2/p0"]).cuda())
+    opt.step()
+    assert torch.equal(p.detach(), p1)

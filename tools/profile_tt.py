@@ -28,3 +28,28 @@ rows.sort(key=lambda x: -x[1])
 print("GPU kernel time per step: %.1f us" % sum(x[1] for x in rows))
 for k, t, c in rows[:20]:
     print("%9.1f us %5.1fx  %s" % (t, c, k[:110]))
+
+from tn_gradient.tt import TensorTrain
+mat = torch.randn(M, N, device=dev)
+for name, fn in (("from_matrix", lambda: TensorTrain.from_matrix(mat, list(ranks))),):
+    for _ in range(3):
+        tt = fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            tt = fn()
+        torch.cuda.synchronize()
+    rows = [(e.key, e.device_time_total / 5, e.count / 5) for e in prof.key_averages() if e.device_time_total > 0]
+    rows.sort(key=lambda x: -x[1])
+    print("%s GPU kernel time per call: %.1f us" % (name, sum(x[1] for x in rows)))
+    for k, t, c in rows[:12]:
+        print("%9.1f us %5.1fx  %s" % (t, c, k[:110]))
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    for _ in range(5):
+        tt.to_matrix((M, N))
+    torch.cuda.synchronize()
+rows = [(e.key, e.device_time_total / 5, e.count / 5) for e in prof.key_averages() if e.device_time_total > 0]
+rows.sort(key=lambda x: -x[1])
+print("to_matrix GPU kernel time per call: %.1f us" % sum(x[1] for x in rows))
+for k, t, c in rows[:8]:
+    print("%9.1f us %5.1fx  %s" % (t, c, k[:110]))
