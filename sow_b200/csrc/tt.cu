@@ -289,7 +289,7 @@ cq_chol_kernel(double* __restrict__ ws, const double* __restrict__ part, int n_p
       weak = weak || (alive && d < 1e-8 * g0[j]);
     }
     if (alive && i > j && i < r) {
-      const double f = A[i][j] / d;
+      const double f = A[i][j] * __drcp_rn(d);     // reciprocal + multiply: the fp64 divide is the longest link of the 64-step chain
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int k = kb + 16 * c;
@@ -1267,8 +1267,19 @@ __device__ __forceinline__ void sts_ct(float* s, const float (&v)[CT]) {
 
 constexpr int kRegTileRows = 32;
 constexpr size_t reg_kernel_smem(int R) { return std::max<size_t>(size_t(2048) * R, 32768); }
+// projection-only instance: three Q' stage buffers; the final reduction scratch is TY * R * 64 floats = 1024 * CT * R bytes
+constexpr size_t reg_proj_smem(int R, int CT) { return std::max<size_t>(size_t(384) * R, size_t(1024) * CT * R); }
+// row-range splits of the register-accumulating kernels: two resident CTAs per SM, two waves
+static int reg_kernel_splits(int P, int* per) {
+  const int n_strips = ceil_div(P, 64), n_rt = ceil_div(P, kRegTileRows);
+  int splits = std::max(1, (2 * 2 * num_sms()) / n_strips);
+  splits = std::min(splits, n_rt);
+  *per = ceil_div(n_rt, splits);
+  return ceil_div(n_rt, *per);
+}
 
-template <typename T, int R, int CT>
+// PROJ: projection only -- R'[r, P] = Q'^T . unfolding(g) (tt_project2: no cores, no Adam, p untouched, one moment).
+template <typename T, int R, int CT, bool PROJ = false>
 __global__ void __launch_bounds__(256, 2)
 tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __restrict__ G1m, const float* __restrict__ G2m,
                     const float* __restrict__ G1v, const float* __restrict__ G2v, int r, const float* __restrict__ Qm,
@@ -1279,14 +1290,16 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
   pdl_wait();
   constexpr int TX = 64 / CT, TY = 256 / TX, RTH = kRegTileRows / TY;
   constexpr int KS = (CT == 4) ? 2 : 4;       // k-step of the reconstruction: 2 . KS . CT operand registers
-  static_assert(2 * R * CT == 64 && TY * R * 64 == 8192, "micro-tile shape");
+  static_assert((PROJ ? 1 : 2) * R * CT <= 64, "accumulator registers");
   constexpr int kArr = kRegTileRows * R;        // floats of one staged array (32 rows x R)
-  constexpr int kBuf = 4 * kArr;                // G1m | G1v | Q'm | Q'v
+  constexpr int kNArr = PROJ ? 1 : 4;           // G1m | G1v | Q'm | Q'v   (PROJ: Q' only)
+  constexpr int kQm = PROJ ? 0 : 2, kQv = 3;
+  constexpr int kBuf = kNArr * kArr;
   using Raw = typename RawVec<T, CT>::type;
   extern __shared__ __align__(16) float fs[];
-  float* s2m = fs;                 // [R][64]  G2m[k][b0 + c]
-  float* s2v = s2m + R * 64;
-  float* stage = s2v + R * 64;     // [3][4][32][R]
+  float* s2m = fs;                 // [R][64]  G2m[k][b0 + c]   (absent in PROJ)
+  float* s2v = s2m + (PROJ ? 0 : R * 64);
+  float* stage = s2v + (PROJ ? 0 : R * 64);     // [3][kNArr][32][R]
   const int P = mm * nn;
   const int tid = threadIdx.x, ty = tid / TX, tx = tid % TX;
   const int b0 = blockIdx.x * 64;
@@ -1294,11 +1307,16 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
   const int t_begin = blockIdx.y * tiles_per_cta;
   const int t_end = min(n_tiles, t_begin + tiles_per_cta);
 
-  float accm[R][CT], accv[R][CT];
+  constexpr int RV = PROJ ? 1 : R;
+  float accm[R][CT], accv[RV][CT];
 #pragma unroll
   for (int k = 0; k < R; ++k)
 #pragma unroll
-    for (int c = 0; c < CT; ++c) accm[k][c] = accv[k][c] = 0.f;
+    for (int c = 0; c < CT; ++c) accm[k][c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < RV; ++k)
+#pragma unroll
+    for (int c = 0; c < CT; ++c) accv[k][c] = 0.f;
 
   // column part of the index map (strip-constant): gb = i2 * nn + o2 -> source (row offset i2, column offset o2).
   // A thread's CT columns cross at most one i2 boundary (nn >= CT is required by the launcher): columns c >= cut sit
@@ -1318,12 +1336,11 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
     constexpr int kChunks = kBuf / 4;            // 16-byte chunks of one buffer
     if (fast) {
 #pragma unroll
-      for (int u = 0; u < kChunks / 256; ++u) {
-        const int q = tid + u * 256;
+      for (int q = tid; q < kChunks; q += 256) {
         const int arr = q / (kArr / 4), w = q - arr * (kArr / 4);
         const int i = w / (R / 4), k4 = w - i * (R / 4);
-        if (first_step && arr < 2) continue;
-        const float* base = arr == 0 ? G1m : (arr == 1 ? G1v : (arr == 2 ? Qm : Qv));
+        if (!PROJ && first_step && arr < 2) continue;
+        const float* base = PROJ ? Qm : (arr == 0 ? G1m : (arr == 1 ? G1v : (arr == 2 ? Qm : Qv)));
         const bool ok = a0 + i < P;
         cp_async16(buf + arr * kArr + i * R + k4 * 4, ok ? base + static_cast<int64_t>(a0 + i) * r + k4 * 4 : base, ok);
       }
@@ -1331,8 +1348,8 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
       for (int q = tid; q < kBuf; q += 256) {
         const int arr = q / kArr, w = q - arr * kArr;
         const int i = w / R, k = w - i * R;
-        if (first_step && arr < 2) continue;
-        const float* base = arr == 0 ? G1m : (arr == 1 ? G1v : (arr == 2 ? Qm : Qv));
+        if (!PROJ && first_step && arr < 2) continue;
+        const float* base = PROJ ? Qm : (arr == 0 ? G1m : (arr == 1 ? G1v : (arr == 2 ? Qm : Qv)));
         buf[q] = (a0 + i < P && k < r) ? base[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
       }
     }
@@ -1340,7 +1357,7 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
 
   if (t_begin < t_end) stage_tile(t_begin, stage);
   cp_async_commit();
-  if (!first_step) {
+  if (!PROJ && !first_step) {
     for (int idx = tid; idx < R * 64; idx += 256) {
       const int kk = idx / 64, c = idx % 64;
       const bool ok = kk < r && b0 + c < P;
@@ -1374,7 +1391,7 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
       if (vec_base && row_ok && row < M && col + CT <= N && (eoff[a] % CT) == 0) {
         vecbits |= 1u << a;
         graw[a] = *reinterpret_cast<const Raw*>(g + eoff[a]);
-        praw[a] = *reinterpret_cast<const Raw*>(p + eoff[a]);
+        if constexpr (!PROJ) praw[a] = *reinterpret_cast<const Raw*>(p + eoff[a]);
       } else {
         // unaligned / boundary rows: element loads, packed like the vector (zeros outside)
         T tg[CT], tp[CT];
@@ -1385,10 +1402,10 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
           const int e = eoff[a] + c + over * hop;
           okbits |= (ok ? 1u : 0u) << (a * CT + c);
           tg[c] = ok ? g[e] : T(0.f);
-          tp[c] = ok ? p[e] : T(0.f);
+          if constexpr (!PROJ) tp[c] = ok ? p[e] : T(0.f);
         }
         memcpy(&graw[a], tg, sizeof(Raw));
-        memcpy(&praw[a], tp, sizeof(Raw));
+        if constexpr (!PROJ) memcpy(&praw[a], tp, sizeof(Raw));
       }
       if (++o1 == nn) o1 = 0, ++i1;
     }
@@ -1402,7 +1419,7 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
     for (int a = 0; a < RTH; ++a)
 #pragma unroll
       for (int c = 0; c < CT; ++c) am[a][c] = av[a][c] = 0.f;
-    if (!first_step) {
+    if (!PROJ && !first_step) {
       const float* s1m = buf + (ty * RTH) * R;
       const float* s1v = buf + kArr + (ty * RTH) * R;
 #pragma unroll
@@ -1442,7 +1459,11 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
       pval = fmaf(-lr_wd, pval, pval);                                         // ttadam.py:110-111 (lr_wd = 0: no-op)
       m_io = mo, v_io = vo;
     };
-    if (vecbits == (1u << RTH) - 1u) {        // the common case: every row of the micro-tile is one aligned vector
+    if constexpr (PROJ) {
+      // the "moment" is the source element itself (zeros outside (M, N) came with the loads)
+#pragma unroll
+      for (int a = 0; a < RTH; ++a) raw_unpack<T, CT>(graw[a], am[a]);
+    } else if (vecbits == (1u << RTH) - 1u) {        // the common case: every row of the micro-tile is one aligned vector
 #pragma unroll
       for (int a = 0; a < RTH; ++a) {
         float gv[CT], pv[CT];
@@ -1474,36 +1495,40 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
 
     // ---- projection: acc[k][c] += Q'[row a, k] . m'[a][c] ----
     {
-      const float* sQm = buf + 2 * kArr + (ty * RTH) * R;
-      const float* sQv = buf + 3 * kArr + (ty * RTH) * R;
+      const float* sQm = buf + kQm * kArr + (ty * RTH) * R;
+      const float* sQv = buf + (PROJ ? 0 : kQv) * kArr + (ty * RTH) * R;
 #pragma unroll
       for (int a = 0; a < RTH; ++a)
 #pragma unroll
         for (int k4 = 0; k4 < R / 4; ++k4) {
           const float4 qm = *reinterpret_cast<const float4*>(sQm + a * R + 4 * k4);
-          const float4 qv = *reinterpret_cast<const float4*>(sQv + a * R + 4 * k4);
-          const float qms[4] = {qm.x, qm.y, qm.z, qm.w}, qvs[4] = {qv.x, qv.y, qv.z, qv.w};
+          const float qms[4] = {qm.x, qm.y, qm.z, qm.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int c = 0; c < CT; ++c) {
-              accm[4 * k4 + j][c] = fmaf(qms[j], am[a][c], accm[4 * k4 + j][c]);
-              accv[4 * k4 + j][c] = fmaf(qvs[j], av[a][c], accv[4 * k4 + j][c]);
-            }
+            for (int c = 0; c < CT; ++c) accm[4 * k4 + j][c] = fmaf(qms[j], am[a][c], accm[4 * k4 + j][c]);
+          if constexpr (!PROJ) {
+            const float4 qv = *reinterpret_cast<const float4*>(sQv + a * R + 4 * k4);
+            const float qvs[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c = 0; c < CT; ++c) accv[4 * k4 + j][c] = fmaf(qvs[j], av[a][c], accv[4 * k4 + j][c]);
+          }
         }
     }
   }
 
   // ---- sum the TY row groups of every column (fixed order) and store this row range's partial of R' ----
   cp_async_wait<0>();
-  float* red = fs;                  // [TY][R][64] floats = 32 KB, over the (dead) staging area
+  float* red = fs;                  // [TY][R][64] floats (32 KB; PROJ: up to 64 KB), over the (dead) staging area
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (PROJ ? 1 : 2); ++pass) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       if (pass == 0) sts_ct<CT>(red + (ty * R + k) * 64 + tx * CT, accm[k]);
-      else sts_ct<CT>(red + (ty * R + k) * 64 + tx * CT, accv[k]);
+      else if constexpr (!PROJ) sts_ct<CT>(red + (ty * R + k) * 64 + tx * CT, accv[k]);
     }
     __syncthreads();
     float* dst = (pass == 0 ? Rm : Rv) + blockIdx.y * split_stride;
@@ -1517,6 +1542,107 @@ tt_adam2_reg_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __r
       if (k < r && b0 + col < P) dst[static_cast<int64_t>(k) * P + b0 + col] = s;
     }
   }
+}
+
+// Reconstruction only, same structure: dst[M, N] = (G1 [P, r] . G2 [r, P]) read back through the index map.  A thread owns
+// 4 rows x 4 columns of a 64 x 64 tile (2 R shared loads per 16 R FMAs, against 8 per 16 in tt_reconstruct2_kernel), the G2
+// strip stays in shared memory for the CTA's whole row range, G1 tiles arrive by cp.async three buffers deep, and the
+// (M, N) window is written with one vector store per row wherever the index map allows it.
+template <typename T, int R>
+__global__ void __launch_bounds__(256, 3)
+tt_reconstruct2_reg_kernel(const float* __restrict__ G1, const float* __restrict__ G2, int r, T* __restrict__ dst, int M, int N,
+                           int mm, int nn, int tiles_per_cta) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int CT = 4, TX = 16, RTH = 4, ROWS = 64;
+  constexpr int kArr = ROWS * R;
+  using Raw = typename RawVec<T, CT>::type;
+  extern __shared__ __align__(16) float fs[];
+  float* s2 = fs;                  // [R][64]  G2[k][b0 + c]
+  float* stage = s2 + R * 64;      // [3][64][R]
+  const int P = mm * nn;
+  const int tid = threadIdx.x, ty = tid / TX, tx = tid % TX;
+  const int b0 = blockIdx.x * 64;
+  const int n_tiles = (P + ROWS - 1) / ROWS;
+  const int t_begin = blockIdx.y * tiles_per_cta;
+  const int t_end = min(n_tiles, t_begin + tiles_per_cta);
+  const int gb0 = b0 + tx * CT;
+  const int ci2 = gb0 / nn, co2 = gb0 - ci2 * nn;
+  const int cut = nn - co2;
+  const int ncols = min(CT, P - gb0);
+  const bool vec_base = cut >= CT && ncols >= CT && (reinterpret_cast<uintptr_t>(dst) % sizeof(Raw)) == 0;
+  const int hop = N - nn;
+  const bool fast = (r == R) && ((reinterpret_cast<uintptr_t>(G1) & 15) == 0);
+  auto stage_tile = [&](int t, float* buf) {
+    const int a0 = t * ROWS;
+    if (fast) {
+      for (int q = tid; q < kArr / 4; q += 256) {
+        const int i = q / (R / 4), k4 = q - i * (R / 4);
+        const bool ok = a0 + i < P;
+        cp_async16(buf + i * R + k4 * 4, ok ? G1 + static_cast<int64_t>(a0 + i) * r + k4 * 4 : G1, ok);
+      }
+    } else {
+      for (int q = tid; q < kArr; q += 256) {
+        const int i = q / R, k = q - i * R;
+        buf[q] = (a0 + i < P && k < r) ? G1[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+      }
+    }
+  };
+  if (t_begin < t_end) stage_tile(t_begin, stage);
+  cp_async_commit();
+  for (int idx = tid; idx < R * 64; idx += 256) {
+    const int kk = idx / 64, c = idx % 64;
+    s2[idx] = (kk < r && b0 + c < P) ? G2[static_cast<int64_t>(kk) * P + b0 + c] : 0.f;
+  }
+  for (int t = t_begin; t < t_end; ++t) {
+    float* buf = stage + ((t - t_begin) % 3) * kArr;
+    if (t + 1 < t_end) stage_tile(t + 1, stage + ((t + 1 - t_begin) % 3) * kArr);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    float acc[RTH][CT];
+#pragma unroll
+    for (int a = 0; a < RTH; ++a)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[a][c] = 0.f;
+    const float* s1 = buf + (ty * RTH) * R;
+#pragma unroll
+    for (int k0 = 0; k0 < R; k0 += 4) {
+      float x2[4][CT];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lds_ct<CT>(s2 + (k0 + j) * 64 + tx * CT, x2[j]);
+#pragma unroll
+      for (int a = 0; a < RTH; ++a) {
+        float x1[4];
+        lds_ct<4>(s1 + a * R + k0, x1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[a][c] = fmaf(x1[j], x2[j][c], acc[a][c]);
+      }
+    }
+    // row ga = i1 * nn + o1 -> source row i1 * mm + i2, column o1 * nn + o2; only the (M, N) window is stored
+    const int ga_first = t * ROWS + ty * RTH;
+    int i1 = ga_first / nn, o1 = ga_first - i1 * nn;
+#pragma unroll
+    for (int a = 0; a < RTH; ++a) {
+      const bool row_ok = ga_first + a < P;
+      const int row = i1 * mm + ci2, col = o1 * nn + co2;
+      const int e0 = row * N + col;
+      if (vec_base && row_ok && row < M && col + CT <= N && (e0 % CT) == 0) {
+        *reinterpret_cast<Raw*>(dst + e0) = raw_pack<T, CT>(acc[a]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          const int over = c >= cut ? 1 : 0;
+          if (row_ok && c < ncols && row + over < M && col + c - over * nn < N)
+            store_from_f32<T>(dst, e0 + c + over * hop, acc[a][c]);
+        }
+      }
+      if (++o1 == nn) o1 = 0, ++i1;
+    }
+  }
+  cp_async_wait<0>();
 }
 
 // Dense variant for order > 2: m, v are fp32 (M, N) work matrices (already reconstructed + de-interleaved).
@@ -1596,11 +1722,8 @@ static int launch_adam2(bool head, void* p, const void* g, const float* G1m, con
       static const bool use_reg = [] { const char* e = getenv("SOWB_TT_REG"); return e == nullptr || atoi(e) != 0; }();
       if (use_reg && nn >= 4 && (int64_t(mm) * mm + 1) * N < (int64_t(1) << 31)) {
         constexpr int CT = 32 / R;
-        const int n_rt = ceil_div(P, kRegTileRows);
-        int splits = std::max(1, (2 * 2 * num_sms()) / n_tiles);     // two resident CTAs per SM, two waves
-        splits = std::min(splits, n_rt);
-        const int per = ceil_div(n_rt, splits);
-        splits = ceil_div(n_rt, per);
+        int per;
+        const int splits = reg_kernel_splits(P, &per);
         const int64_t rp = int64_t(r) * P;
         float* dm = Rm;
         float* dv = Rv;
@@ -1662,6 +1785,48 @@ static int dispatch_adam2(bool head, void* p, const void* g, const float* G1m, c
   if (r <= 32) SOWB_ADAM2(32);
   SOWB_ADAM2(64);
 #undef SOWB_ADAM2
+}
+
+// tt_project2 through the register-accumulating kernel (projection only).  part: [splits][r][P] partials when splits > 1
+template <typename T, int R, int CT>
+static int launch_project2_reg(const T* src, int M, int N, int mm, int nn, const float* Q, float* Rout, int r, float* part,
+                               size_t part_bytes, cudaStream_t stream) {
+  const int P = mm * nn;
+  int per;
+  const int splits = reg_kernel_splits(P, &per);
+  const int64_t rp = int64_t(r) * P;
+  float* dst = Rout;
+  if (splits > 1) {
+    const size_t need = size_t(splits) * rp * sizeof(float);
+    if (part == nullptr || part_bytes < need)
+      return set_error(SOWB_EWORKSPACE, "tt_project2: workspace %zu B < required %zu B (tt_project2_workspace_bytes)", part_bytes, need);
+    dst = part;
+  }
+  auto k = tt_adam2_reg_kernel<T, R, CT, true>;
+  constexpr size_t smem = reg_proj_smem(R, CT);
+  SOWB_CHECK_CUDA(set_max_smem_once(k, smem));
+  T* no_p = nullptr;
+  const float* nf = nullptr;
+  float* nfm = nullptr;
+  SOWB_CHECK_CUDA(launch_pdl(k, dim3(ceil_div(P, 64), splits), dim3(256), smem, stream, no_p, src, nf, nf, nf, nf, r, Q, nf, dst,
+                             nfm, M, N, mm, nn, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1, per, splits > 1 ? rp : int64_t(0)));
+  if (splits > 1) return launch_sum_splits(part, splits, rp, 0, Rout, 0, rp, 1, stream);
+  return SOWB_OK;
+}
+
+template <typename T>
+static int dispatch_project2_reg(const T* src, int M, int N, int mm, int nn, const float* Q, float* Rout, int r, float* part,
+                                 size_t part_bytes, cudaStream_t stream) {
+  if (r <= 8) return launch_project2_reg<T, 8, 4>(src, M, N, mm, nn, Q, Rout, r, part, part_bytes, stream);
+  if (r <= 16) return launch_project2_reg<T, 16, 4>(src, M, N, mm, nn, Q, Rout, r, part, part_bytes, stream);
+  return launch_project2_reg<T, 32, 2>(src, M, N, mm, nn, Q, Rout, r, part, part_bytes, stream);
+}
+
+static bool project2_reg_ok(int N, int mm, int nn, int r) {
+  static const bool enabled = [] { const char* e = getenv("SOWB_TT_REG"); return e == nullptr || atoi(e) != 0; }();
+  // measured at 4096^2 fp32: 21 / 29 / 46 us at r = 8 / 16 / 32 against 83-85 us for the tiled kernel; r = 64 (one column per
+  // thread) 133 us against 89 us: the tiled kernel keeps the ranks above 32
+  return enabled && r <= 32 && nn >= 4 && (int64_t(mm) * mm + 1) * N < (int64_t(1) << 31);
 }
 
 }  // namespace sowb
@@ -1876,7 +2041,10 @@ int tt_gather2(const void* src, int M, int N, int mm, int nn, float* X, int ncol
 
 size_t tt_project2_workspace_bytes(int mm, int nn, int r) {
   if (mm <= 0 || nn <= 0 || r <= 0) return 0;
-  return tt_project_workspace_bytes(mm * nn, mm * nn, r, 1);
+  int per;
+  const int reg_splits = reg_kernel_splits(mm * nn, &per);
+  const size_t reg_bytes = reg_splits > 1 ? size_t(reg_splits) * r * mm * nn * sizeof(float) : 0;
+  return std::max(reg_bytes, tt_project_workspace_bytes(mm * nn, mm * nn, r, 1));     // either kernel may run
 }
 
 int tt_project2(const void* src, int M, int N, int mm, int nn, const float* Q, float* R, int r, int dtype, void* ws,
@@ -1887,6 +2055,12 @@ int tt_project2(const void* src, int M, int N, int mm, int nn, const float* Q, f
   if (int rc0 = ensure_context_for(src)) return rc0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int P = mm * nn;
+  if (project2_reg_ok(N, mm, nn, r)) {
+    // ranks <= 32: the projection accumulates in registers (the tiled kernel below spends a 64-row rank tile on any rank)
+    if (dtype == SOWB_BF16)
+      return dispatch_project2_reg(static_cast<const __nv_bfloat16*>(src), M, N, mm, nn, Q, R, r, static_cast<float*>(ws), ws_bytes, stream);
+    return dispatch_project2_reg(static_cast<const float*>(src), M, N, mm, nn, Q, R, r, static_cast<float*>(ws), ws_bytes, stream);
+  }
   const int n_tiles = ceil_div(P, kPjTN);
   int m_per;
   const int splits = project_splits(P, n_tiles, 1, &m_per);
@@ -1915,6 +2089,35 @@ int tt_reconstruct2(const float* G1, const float* G2, int r, void* dst, int M, i
   if (int rc0 = ensure_context_for(G1)) return rc0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int P = mm * nn;
+  SOWB_REQUIRE(dtype == SOWB_BF16 || dtype == SOWB_F32, "tt_reconstruct2: unknown dtype %d", dtype);
+  static const bool use_reg = [] { const char* e = getenv("SOWB_TT_REG"); return e == nullptr || atoi(e) != 0; }();
+  if (use_reg && r <= 64 && nn >= 4 && (int64_t(mm) * mm + 1) * N < (int64_t(1) << 31)) {
+    // strips x row ranges: three resident CTAs per SM, about two waves
+    const int n_strips = ceil_div(P, 64), n_rt = ceil_div(P, 64);
+    int splits = std::min(n_rt, std::max(1, (2 * 3 * num_sms()) / n_strips));
+    const int per = ceil_div(n_rt, splits);
+    splits = ceil_div(n_rt, per);
+    const dim3 rgrid(n_strips, splits);
+#define SOWB_RECON(TT, RR)                                                                                              \
+  do {                                                                                                                  \
+    auto k = tt_reconstruct2_reg_kernel<TT, RR>;                                                                        \
+    constexpr size_t smem = size_t(1024) * RR;                                                                          \
+    SOWB_CHECK_CUDA(set_max_smem_once(k, smem));                                                                        \
+    SOWB_CHECK_CUDA(launch_pdl(k, rgrid, dim3(256), smem, stream, G1, G2, r, static_cast<TT*>(dst), M, N, mm, nn, per)); \
+    return SOWB_OK;                                                                                                     \
+  } while (0)
+#define SOWB_RECON_R(TT)        \
+  do {                          \
+    if (r <= 8) SOWB_RECON(TT, 8);   \
+    if (r <= 16) SOWB_RECON(TT, 16); \
+    if (r <= 32) SOWB_RECON(TT, 32); \
+    SOWB_RECON(TT, 64);              \
+  } while (0)
+    if (dtype == SOWB_BF16) SOWB_RECON_R(__nv_bfloat16);
+    SOWB_RECON_R(float);
+#undef SOWB_RECON_R
+#undef SOWB_RECON
+  }
   dim3 grid(ceil_div(P, kRkTile), ceil_div(P, kRkTile));
   SOWB_REQUIRE(grid.y <= 65535, "tt_reconstruct2: unfolding too large");
   if (dtype == SOWB_BF16)
