@@ -3,7 +3,8 @@ tn_gradient/optimizer/ttadam.py, ttsgd.py) plus the fused multi-tensor AdamW use
 
 TTAdam keeps the reference's state layout (``step``, ``exp_avg``, ``exp_avg_sq`` as TensorTrain objects after a
 step with "ranks", ``exp_avg_expr`` / ``exp_avg_sq_expr``) but executes each parameter's update as
-    order 2 : tt_adam_fused2 (reconstruct m, v + Adam + write padded/interleaved m', v')  ->  thin-QR + projection
+    order 2 : tt_adam2_step through a per-parameter ops.TTAdam2Plan (head -> thin QR -> fused reconstruct + Adam + projection;
+              the dense moments never reach HBM; rank > 64: tt_adam_fused2 -> thin-QR + projection)
     order>2 : tt_matmul_rk chain + tt_deinterleave -> tt_adam_dense -> tt_interleave -> thin-QR + projection sweep
 instead of ~8 elementwise launches, two einsum reconstructions and two complete QRs.
 """
