@@ -1696,6 +1696,81 @@ __global__ void tt_adam_interleaved_kernel(T* __restrict__ p, const T* __restric
   }
 }
 
+// Four consecutive interleaved positions per thread (nn % 4 == 0: they differ in the last output digit only, so they are
+// four consecutive columns of one source row): one index decode per four elements, 16-byte accesses on the interleaved
+// side and one vector access on the (M, N) side when N % 4 == 0.  MODE 0: interleave (src -> out4), 1: de-interleave
+// (in4 -> dst), 2: the TT-Adam update of tt_adam_interleaved_kernel.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+tt_interleaved_vec4_kernel(T* __restrict__ p, const T* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int M,
+                           int N, FastDiv fm, FastDiv fn, int order, uint32_t total4, float beta1, float omb1, float beta2,
+                           float omb2, float eps, float step_size, float lr_wd) {
+  using Raw = typename RawVec<T, 4>::type;
+  const bool src_vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) % sizeof(Raw)) == 0;
+  for (uint32_t i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += gridDim.x * blockDim.x) {
+    const uint32_t idx = i4 * 4;
+    int64_t row, col;
+    decode_interleaved(idx, fm, fn, order, row, col);
+    const bool row_ok = row < M;
+    const int64_t left = N - col;
+    const int ncol = row_ok ? static_cast<int>(left < 4 ? left : 4) : 0;      // valid columns (<= 0: none)
+    const int64_t e = row * N + col;
+    const bool vec = src_vec && ncol == 4;
+    float gv[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE != 1) {
+      if (vec) {
+        raw_unpack<T, 4>(*reinterpret_cast<const Raw*>(g + e), gv);
+        if (MODE == 2) raw_unpack<T, 4>(*reinterpret_cast<const Raw*>(p + e), pv);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < ncol) {
+            gv[c] = load_as_f32<T>(g, e + c);
+            if (MODE == 2) pv[c] = load_as_f32<T>(p, e + c);
+          }
+      }
+    }
+    if (MODE == 0) {
+      *reinterpret_cast<float4*>(m + idx) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      continue;
+    }
+    const float4 m4 = *reinterpret_cast<const float4*>(m + idx);
+    float mo[4] = {m4.x, m4.y, m4.z, m4.w};
+    if (MODE == 2) {
+      const float4 v4 = *reinterpret_cast<const float4*>(v + idx);
+      float vo[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < ncol) {
+          mo[c] = beta1 * mo[c] + omb1 * gv[c];                                   // ttadam.py:92
+          vo[c] = beta2 * fmaxf(vo[c], 0.f) + omb2 * gv[c] * gv[c];               // ttadam.py:84,93
+          pv[c] -= step_size * (mo[c] / (sqrtf(vo[c]) + eps));                    // ttadam.py:94,103,108
+          if (lr_wd > 0.f) pv[c] -= lr_wd * pv[c];                                // ttadam.py:110-111
+        } else {
+          mo[c] = vo[c] = 0.f;                                                    // padded positions
+        }
+      }
+      *reinterpret_cast<float4*>(m + idx) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+      *reinterpret_cast<float4*>(v + idx) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pv[c] = mo[c];
+    }
+    if (vec) {
+      *reinterpret_cast<Raw*>(p + e) = raw_pack<T, 4>(pv);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < ncol) store_from_f32<T>(p, e + c, pv[c]);
+    }
+  }
+}
+
+// the vec4 kernels apply when the last output digit runs over a multiple of 4 and 32-bit indices suffice
+static inline bool interleaved_vec4_ok(int nn, int64_t total, const void* a, const void* b) {
+  return nn % 4 == 0 && total < (int64_t(1) << 32) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
 static inline int grid_for(int64_t n, int threads) {
   const int64_t b = (n + threads - 1) / threads;
   return static_cast<int>(std::min<int64_t>(b, int64_t(num_sms()) * 16));
@@ -2137,6 +2212,20 @@ int tt_interleave(const void* src, int M, int N, int mm, int nn, int order, floa
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int64_t total = 1;
   for (int k = 0; k < order; ++k) total *= int64_t(mm) * nn;
+  if (interleaved_vec4_ok(nn, total, out, nullptr) && (dtype == SOWB_BF16 || dtype == SOWB_F32)) {
+    const uint32_t total4 = static_cast<uint32_t>(total / 4);
+    float* nf = nullptr;
+    if (dtype == SOWB_BF16)
+      tt_interleaved_vec4_kernel<__nv_bfloat16, 0><<<grid_for(total4, 256), 256, 0, stream>>>(
+          nullptr, static_cast<const __nv_bfloat16*>(src), out, nf, M, N, make_fastdiv(mm), make_fastdiv(nn), order, total4, 0.f, 0.f,
+          0.f, 0.f, 0.f, 0.f, 0.f);
+    else
+      tt_interleaved_vec4_kernel<float, 0><<<grid_for(total4, 256), 256, 0, stream>>>(
+          nullptr, static_cast<const float*>(src), out, nf, M, N, make_fastdiv(mm), make_fastdiv(nn), order, total4, 0.f, 0.f, 0.f,
+          0.f, 0.f, 0.f, 0.f);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    return SOWB_OK;
+  }
   if (dtype == SOWB_BF16)
     tt_interleave_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), M, N, make_fastdiv(mm), make_fastdiv(nn), order, out, total);
   else if (dtype == SOWB_F32)
@@ -2154,6 +2243,21 @@ int tt_deinterleave(const float* src, int M, int N, int mm, int nn, int order, v
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int64_t total = 1;
   for (int k = 0; k < order; ++k) total *= int64_t(mm) * nn;
+  if (interleaved_vec4_ok(nn, total, src, nullptr) && (dtype == SOWB_BF16 || dtype == SOWB_F32)) {
+    const uint32_t total4 = static_cast<uint32_t>(total / 4);
+    float* in = const_cast<float*>(src);       // MODE 1 only reads it
+    float* nf = nullptr;
+    if (dtype == SOWB_BF16)
+      tt_interleaved_vec4_kernel<__nv_bfloat16, 1><<<grid_for(total4, 256), 256, 0, stream>>>(
+          static_cast<__nv_bfloat16*>(out), nullptr, in, nf, M, N, make_fastdiv(mm), make_fastdiv(nn), order, total4, 0.f, 0.f, 0.f,
+          0.f, 0.f, 0.f, 0.f);
+    else
+      tt_interleaved_vec4_kernel<float, 1><<<grid_for(total4, 256), 256, 0, stream>>>(
+          static_cast<float*>(out), nullptr, in, nf, M, N, make_fastdiv(mm), make_fastdiv(nn), order, total4, 0.f, 0.f, 0.f, 0.f, 0.f,
+          0.f, 0.f);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    return SOWB_OK;
+  }
   if (dtype == SOWB_BF16)
     tt_deinterleave_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(src, M, N, make_fastdiv(mm), make_fastdiv(nn), order, static_cast<__nv_bfloat16*>(out), total);
   else if (dtype == SOWB_F32)
@@ -2218,6 +2322,19 @@ int tt_adam_interleaved(void* p, const void* g, float* m, float* v, int M, int N
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int64_t total = 1;
   for (int k = 0; k < order; ++k) total *= int64_t(mm) * nn;
+  if (interleaved_vec4_ok(nn, total, m, v) && (dtype == SOWB_BF16 || dtype == SOWB_F32)) {
+    const uint32_t total4 = static_cast<uint32_t>(total / 4);
+    if (dtype == SOWB_BF16)
+      tt_interleaved_vec4_kernel<__nv_bfloat16, 2><<<grid_for(total4, 256), 256, 0, stream>>>(
+          static_cast<__nv_bfloat16*>(p), static_cast<const __nv_bfloat16*>(g), m, v, M, N, make_fastdiv(mm), make_fastdiv(nn), order,
+          total4, beta1, omb1, beta2, omb2, eps, step_size, lr_wd);
+    else
+      tt_interleaved_vec4_kernel<float, 2><<<grid_for(total4, 256), 256, 0, stream>>>(
+          static_cast<float*>(p), static_cast<const float*>(g), m, v, M, N, make_fastdiv(mm), make_fastdiv(nn), order, total4, beta1,
+          omb1, beta2, omb2, eps, step_size, lr_wd);
+    SOWB_CHECK_CUDA(cudaGetLastError());
+    return SOWB_OK;
+  }
   if (dtype == SOWB_BF16)
     tt_adam_interleaved_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
         static_cast<__nv_bfloat16*>(p), static_cast<const __nv_bfloat16*>(g), m, v, M, N, make_fastdiv(mm), make_fastdiv(nn),
