@@ -158,6 +158,7 @@ thin_qr_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kCqMaxR = 64;
 constexpr int kCqRows = 128;
+constexpr int kCqGramRows = 64;    // rows per Gram block: the fp64 pipe is narrow, so the work is spread over more SMs
 constexpr size_t kCqWsPerBatch = (kCqMaxR * kCqMaxR + kCqMaxR) * sizeof(double);
 
 // Gram partials: CTA (x, b) accumulates X_b[rows]^T X_b[rows] in fp64 over the 128-row blocks x, x + gridDim.x, ... (fixed
@@ -172,7 +173,7 @@ cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __res
   pdl_trigger();
   pdl_wait();
   if (only_if != nullptr && only_if[blockIdx.y] == 0) return;      // second pass: flagged matrices only
-  __shared__ float sx[kCqRows][kCqMaxR + 1];
+  __shared__ float sx[kCqGramRows][kCqMaxR + 1];
   const float* Xb = X + blockIdx.y * x_bs;
   double* G = part + (static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x) * (r * r);
   const int tid = threadIdx.x;
@@ -182,8 +183,8 @@ cq_gram_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __res
   for (int a = 0; a < RT; ++a)
 #pragma unroll
     for (int c = 0; c < RT; ++c) acc[a][c] = 0.0;
-  for (int row0 = blockIdx.x * kCqRows; row0 < m; row0 += gridDim.x * kCqRows) {
-    const int rows = min(kCqRows, m - row0);
+  for (int row0 = blockIdx.x * kCqGramRows; row0 < m; row0 += gridDim.x * kCqGramRows) {
+    const int rows = min(kCqGramRows, m - row0);
     __syncthreads();
     for (int idx = tid; idx < rows * r; idx += 256) {
       const int i = idx / r, k = idx - i * r;
@@ -372,6 +373,10 @@ cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __res
     Qb[static_cast<int64_t>(row0 + i) * r + k] = sx[i][k];
   }
 }
+
+// Measured and dropped: a variant blocked by 8 columns (finished q_k in shared memory, dynamic loop over the finished columns,
+// only the 8 x 8 triangle unrolled; 64 rows per CTA).  Same 32 us for 2 x 4096 x 64 and 0.91 ms instead of 0.69 ms for the
+// 168 x 2736 x 50 re-initialisation batch: the fp64 FMA rate of the CUDA cores bounds both, not instruction fetch.
 
 // ------------------------------------------------------------------------------------------------
 // projection R[r, n] = Q[m, r]^T L[m, n]    (fp32, register-tiled; split over m into per-split partials that
@@ -1971,7 +1976,7 @@ static CqPlan cq_plan(int m, int r, int batch) {
   pl.ok = r <= kCqMaxR && m >= 64 && batch <= 65535;
   if (!pl.ok) return pl;
   // enough CTAs for about two waves, never more than the 128-row blocks of one matrix
-  pl.n_part = std::max(1, std::min(ceil_div(m, kCqRows), ceil_div(2 * num_sms(), batch)));
+  pl.n_part = std::max(1, std::min(ceil_div(m, kCqGramRows), ceil_div(2 * num_sms(), batch)));
   pl.g_bytes = size_t(batch) * kCqWsPerBatch;
   pl.flag_off = (2 * pl.g_bytes + 15) & ~size_t(15);
   pl.part_off = (pl.flag_off + size_t(batch) * sizeof(int) + 15) & ~size_t(15);
