@@ -245,7 +245,21 @@ int tt_adam2_step(void* p, const void* g, const float* G1m, const float* G2m, co
 int tt_adam_interleaved(void* p, const void* g, float* m, float* v, int M, int N, int mm, int nn, int order, double beta1,
                         double beta2, double eps, double step_size, double lr_wd, int dtype, void* stream);
 
-/* Same update on dense fp32 moments m, v of shape (M,N) (order > 2 path); v is clamped at 0 first (ttadam.py:84). */
+/*
+ * The whole TT-Adam step of an order >= 3 tensor train in ONE call (TTAdam.step, ttadam.py:61-115, for "ranks" of length
+ * order + 1 > 3): reconstruction chain of both moments into the interleaved layout (tt.py:213-237), the interleaved Adam
+ * update of p (tt_adam_interleaved), and one decomposition sweep over both moments as a batch of two (tt.py:111-140).
+ *   cores_in[k] / cores_out[k], k < order : the k-th core of BOTH moments, [2][r_k * P * r_{k+1}] fp32 (m first), P = mm*nn;
+ *                                           cores_in may be NULL on the first step (zero moments).
+ *   ranks[order + 1] with ranks[0] = ranks[order] = 1, inner ranks <= 64.
+ * ws: tt_adam_nd_workspace_bytes(...) bytes (0 = unsupported shape), 256-byte aligned.
+ */
+size_t tt_adam_nd_workspace_bytes(int mm, int nn, int order, const int* ranks);
+int tt_adam_nd_step(void* p, const void* g, const float* const* cores_in, float* const* cores_out, const int* ranks, int M, int N,
+                  int mm, int nn, int order, double beta1, double beta2, double eps, double step_size, double lr_wd,
+                  int first_step, int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* Same update on dense fp32 moments m, v of shape (M,N) (no "ranks": the dense branch); v is clamped at 0 first (ttadam.py:84). */
 int tt_adam_dense(void* p, const void* g, float* m, float* v, int64_t numel, double beta1, double beta2, double eps,
                   double step_size, double lr_wd, int dtype, void* stream);
 

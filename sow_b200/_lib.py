@@ -92,6 +92,8 @@ SIGNATURES = {
                             _vp, _sz, _vp]),
     "tt_adam2_fused_workspace_bytes": (_sz, [_i, _i]),
     "tt_adam2_workspace_bytes": (_sz, [_i, _i]),
+    "tt_adam_nd_workspace_bytes": (_sz, [_i, _i, _i, _vp]),
+    "tt_adam_nd_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i, _vp, _sz, _vp]),
     "tt_adam2_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i,
                            _vp, _sz, _vp]),
     "tt_adam_interleaved": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _vp]),

@@ -1650,6 +1650,192 @@ tt_reconstruct2_reg_kernel(const float* __restrict__ G1, const float* __restrict
   cp_async_wait<0>();
 }
 
+// Dense relatives of the two kernels above for the order > 2 chains (no index map): same micro-tiles and staging.
+//   tt_matmul_rk_reg_kernel : C[m, n] = A[m, r] . B[r, n]                       (r <= 64; reconstruction chain, tt.py:213-237)
+//   tt_project_reg_kernel   : R[r, n] (per split) = Q[rows, r]^T . L[rows, n]   (r <= 32; decomposition sweep, tt.py:129-133)
+template <int R>
+__global__ void __launch_bounds__(256, 3)
+tt_matmul_rk_reg_kernel(const float* __restrict__ A, const float* __restrict__ B, int r, float* __restrict__ C, int m, int n,
+                        int tiles_per_cta) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int CT = 4, TX = 16, RTH = 4, ROWS = 64;
+  constexpr int kArr = ROWS * R;
+  extern __shared__ __align__(16) float fs[];
+  float* s2 = fs;                  // [R][64]  B[k][b0 + c]
+  float* stage = s2 + R * 64;      // [3][64][R]
+  const int tid = threadIdx.x, ty = tid / TX, tx = tid % TX;
+  const int b0 = blockIdx.x * 64;
+  const int n_tiles = (m + ROWS - 1) / ROWS;
+  const int t_begin = blockIdx.y * tiles_per_cta;
+  const int t_end = min(n_tiles, t_begin + tiles_per_cta);
+  const int gb0 = b0 + tx * CT;
+  const int ncols = min(CT, n - gb0);
+  const bool vec_base = ncols >= CT && (n % 4 == 0) && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+  const bool fast = (r == R) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  auto stage_tile = [&](int t, float* buf) {
+    const int a0 = t * ROWS;
+    if (fast) {
+      for (int q = tid; q < kArr / 4; q += 256) {
+        const int i = q / (R / 4), k4 = q - i * (R / 4);
+        const bool ok = a0 + i < m;
+        cp_async16(buf + i * R + k4 * 4, ok ? A + static_cast<int64_t>(a0 + i) * r + k4 * 4 : A, ok);
+      }
+    } else {
+      for (int q = tid; q < kArr; q += 256) {
+        const int i = q / R, k = q - i * R;
+        buf[q] = (a0 + i < m && k < r) ? A[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+      }
+    }
+  };
+  if (t_begin < t_end) stage_tile(t_begin, stage);
+  cp_async_commit();
+  for (int idx = tid; idx < R * 64; idx += 256) {
+    const int kk = idx / 64, c = idx % 64;
+    s2[idx] = (kk < r && b0 + c < n) ? B[static_cast<int64_t>(kk) * n + b0 + c] : 0.f;
+  }
+  for (int t = t_begin; t < t_end; ++t) {
+    float* buf = stage + ((t - t_begin) % 3) * kArr;
+    if (t + 1 < t_end) stage_tile(t + 1, stage + ((t + 1 - t_begin) % 3) * kArr);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    float acc[RTH][CT];
+#pragma unroll
+    for (int a = 0; a < RTH; ++a)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[a][c] = 0.f;
+    const float* s1 = buf + (ty * RTH) * R;
+#pragma unroll
+    for (int k0 = 0; k0 < R; k0 += 4) {
+      float x2[4][CT];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lds_ct<CT>(s2 + (k0 + j) * 64 + tx * CT, x2[j]);
+#pragma unroll
+      for (int a = 0; a < RTH; ++a) {
+        float x1[4];
+        lds_ct<4>(s1 + a * R + k0, x1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[a][c] = fmaf(x1[j], x2[j][c], acc[a][c]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < RTH; ++a) {
+      const int ga = t * ROWS + ty * RTH + a;
+      if (ga >= m) continue;
+      float* dst = C + static_cast<int64_t>(ga) * n + gb0;
+      if (vec_base) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (c < ncols) dst[c] = acc[a][c];
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int R, int CT>
+__global__ void __launch_bounds__(256, 2)
+tt_project_reg_kernel(const float* __restrict__ L, int64_t l_bs, const float* __restrict__ Q, int64_t q_bs, float* __restrict__ Rout,
+                      int64_t r_bs, int64_t split_stride, int rows, int n, int r, int tiles_per_cta) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int TX = 64 / CT, TY = 256 / TX, RTH = kRegTileRows / TY;
+  static_assert(R * CT <= 64, "accumulator registers");
+  constexpr int kArr = kRegTileRows * R;
+  extern __shared__ __align__(16) float fs[];
+  float* stage = fs;               // [3][32][R]
+  const float* Lb = L + blockIdx.z * l_bs;
+  const float* Qb = Q + blockIdx.z * q_bs;
+  float* Rb = Rout + blockIdx.z * r_bs + blockIdx.y * split_stride;
+  const int tid = threadIdx.x, ty = tid / TX, tx = tid % TX;
+  const int b0 = blockIdx.x * 64;
+  const int n_tiles = (rows + kRegTileRows - 1) / kRegTileRows;
+  const int t_begin = blockIdx.y * tiles_per_cta;
+  const int t_end = min(n_tiles, t_begin + tiles_per_cta);
+  const int gb0 = b0 + tx * CT;
+  const int ncols = min(CT, n - gb0);
+  const bool vec = ncols >= CT && (n % CT == 0) && (reinterpret_cast<uintptr_t>(Lb) % (CT * 4)) == 0;
+  const bool fast = (r == R) && ((reinterpret_cast<uintptr_t>(Qb) & 15) == 0);
+  float acc[R][CT];
+#pragma unroll
+  for (int k = 0; k < R; ++k)
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[k][c] = 0.f;
+  auto stage_tile = [&](int t, float* buf) {
+    const int a0 = t * kRegTileRows;
+    if (fast) {
+      for (int q = tid; q < kArr / 4; q += 256) {
+        const int i = q / (R / 4), k4 = q - i * (R / 4);
+        const bool ok = a0 + i < rows;
+        cp_async16(buf + i * R + k4 * 4, ok ? Qb + static_cast<int64_t>(a0 + i) * r + k4 * 4 : Qb, ok);
+      }
+    } else {
+      for (int q = tid; q < kArr; q += 256) {
+        const int i = q / R, k = q - i * R;
+        buf[q] = (a0 + i < rows && k < r) ? Qb[static_cast<int64_t>(a0 + i) * r + k] : 0.f;
+      }
+    }
+  };
+  if (t_begin < t_end) stage_tile(t_begin, stage);
+  cp_async_commit();
+  for (int t = t_begin; t < t_end; ++t) {
+    float* buf = stage + ((t - t_begin) % 3) * kArr;
+    if (t + 1 < t_end) stage_tile(t + 1, stage + ((t + 1 - t_begin) % 3) * kArr);
+    cp_async_commit();
+    float x[RTH][CT];
+#pragma unroll
+    for (int a = 0; a < RTH; ++a) {
+      const int ga = t * kRegTileRows + ty * RTH + a;
+      const float* src = Lb + static_cast<int64_t>(ga) * n + gb0;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) x[a][c] = 0.f;
+      if (ga < rows) {
+        if (vec) {
+          lds_ct<CT>(src, x[a]);       // plain vector load (the helper is address-space agnostic)
+        } else {
+#pragma unroll
+          for (int c = 0; c < CT; ++c)
+            if (c < ncols) x[a][c] = src[c];
+        }
+      }
+    }
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* sQ = buf + (ty * RTH) * R;
+#pragma unroll
+    for (int a = 0; a < RTH; ++a)
+#pragma unroll
+      for (int k4 = 0; k4 < R / 4; ++k4) {
+        const float4 q = *reinterpret_cast<const float4*>(sQ + a * R + 4 * k4);
+        const float qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[4 * k4 + j][c] = fmaf(qs[j], x[a][c], acc[4 * k4 + j][c]);
+      }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  float* red = fs;                  // [TY][R][64] floats over the (dead) staging area
+#pragma unroll
+  for (int k = 0; k < R; ++k) sts_ct<CT>(red + (ty * R + k) * 64 + tx * CT, acc[k]);
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < R * 64 / 256; ++u) {
+    const int o = tid + u * 256;
+    const int k = o / 64, col = o % 64;
+    float sum = 0.f;
+#pragma unroll
+    for (int y = 0; y < TY; ++y) sum += red[(y * R + k) * 64 + col];
+    if (k < r && b0 + col < n) Rb[static_cast<int64_t>(k) * n + b0 + col] = sum;
+  }
+}
+
 // Dense variant for order > 2: m, v are fp32 (M, N) work matrices (already reconstructed + de-interleaved).
 template <typename T>
 __global__ void tt_adam_dense_kernel(T* __restrict__ p, const T* __restrict__ g, float* __restrict__ m,
@@ -2071,11 +2257,31 @@ static int project_splits(int m, int n_tiles, int batch, int* m_per) {
   return ceil_div(m, *m_per);
 }
 
+// row-range splits of tt_project_reg_kernel: two resident CTAs per SM, about two waves over (strips x batch)
+static int project_reg_splits(int m, int n, int batch, int* per) {
+  const int n_strips = ceil_div(n, 64), n_rt = ceil_div(m, kRegTileRows);
+  int splits = std::max(1, (2 * 2 * num_sms()) / std::max(1, n_strips * batch));
+  splits = std::min(std::min(splits, n_rt), 65535);
+  *per = ceil_div(n_rt, splits);
+  return ceil_div(n_rt, *per);
+}
+
+static bool project_reg_ok(int n, int r, int batch) {
+  static const bool enabled = [] { const char* e = getenv("SOWB_TT_REG"); return e == nullptr || atoi(e) != 0; }();
+  return enabled && r <= 32 && batch <= 65535 && ceil_div(n, 64) <= 2147483647;
+}
+
 size_t tt_project_workspace_bytes(int m, int n, int r, int batch) {
   if (m <= 0 || n <= 0 || r <= 0 || batch <= 0) return 0;
   int m_per;
   const int splits = project_splits(m, ceil_div(n, kPjTN), batch, &m_per);
-  return splits > 1 ? size_t(batch) * splits * r * n * sizeof(float) : 0;
+  size_t bytes = splits > 1 ? size_t(batch) * splits * r * n * sizeof(float) : 0;
+  if (project_reg_ok(n, r, batch)) {
+    int per;
+    const int rs = project_reg_splits(m, n, batch, &per);
+    if (rs > 1) bytes = std::max(bytes, size_t(batch) * rs * r * n * sizeof(float));
+  }
+  return bytes;
 }
 
 int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q_batch_stride, float* R,
@@ -2084,6 +2290,35 @@ int tt_project(const float* L, int64_t l_batch_stride, const float* Q, int64_t q
   if (int rc0 = ensure_context_for(L)) return rc0;
   SOWB_REQUIRE(m > 0 && n > 0 && r > 0 && batch > 0, "tt_project: bad dimensions");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (project_reg_ok(n, r, batch)) {
+    // ranks <= 32: projection accumulated in registers (the tiled kernel below spends a 64-row rank tile on any rank)
+    int per;
+    const int splits = project_reg_splits(m, n, batch, &per);
+    const int64_t rn = int64_t(r) * n;
+    float* dst = R;
+    int64_t dst_bs = r_batch_stride, sstride = 0;
+    if (splits > 1) {
+      const size_t need = size_t(batch) * splits * rn * sizeof(float);
+      if (ws == nullptr || ws_bytes < need)
+        return set_error(SOWB_EWORKSPACE, "tt_project: workspace %zu B < required %zu B (tt_project_workspace_bytes)", ws_bytes, need);
+      dst = static_cast<float*>(ws), dst_bs = splits * rn, sstride = rn;
+    }
+    const dim3 rgrid(ceil_div(n, 64), splits, batch);
+#define SOWB_PJREG(RR, CC)                                                                                             \
+  do {                                                                                                                 \
+    auto k = tt_project_reg_kernel<RR, CC>;                                                                            \
+    constexpr size_t smem = std::max<size_t>(size_t(384) * RR, size_t(1024) * CC * RR);                                \
+    SOWB_CHECK_CUDA(set_max_smem_once(k, smem));                                                                       \
+    SOWB_CHECK_CUDA(launch_pdl(k, rgrid, dim3(256), smem, stream, L, l_batch_stride, Q, q_batch_stride, dst, dst_bs,   \
+                               sstride, m, n, r, per));                                                                \
+  } while (0)
+    if (r <= 8) SOWB_PJREG(8, 4);
+    else if (r <= 16) SOWB_PJREG(16, 4);
+    else SOWB_PJREG(32, 2);
+#undef SOWB_PJREG
+    if (splits > 1) return launch_sum_splits(dst, splits, rn, splits * rn, R, r_batch_stride, rn, batch, stream);
+    return SOWB_OK;
+  }
   const int n_tiles = ceil_div(n, kPjTN);
   int m_per;
   const int splits = project_splits(m, n_tiles, batch, &m_per);
@@ -2278,6 +2513,28 @@ int tt_matmul_rk(const float* A, const float* B, float* C, int m, int n, int r, 
   if (int rc0 = ensure_context_for(A)) return rc0;
   SOWB_REQUIRE(m > 0 && n > 0 && r > 0, "tt_matmul_rk: bad dimensions");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  static const bool use_reg = [] { const char* e = getenv("SOWB_TT_REG"); return e == nullptr || atoi(e) != 0; }();
+  if (use_reg && r <= 64) {
+    const int n_strips = ceil_div(n, 64), n_rt = ceil_div(m, 64);
+    int splits = std::min(n_rt, std::max(1, (2 * 3 * num_sms()) / n_strips));
+    splits = std::min(splits, 65535);
+    const int per = ceil_div(n_rt, splits);
+    splits = ceil_div(n_rt, per);
+    const dim3 rgrid(n_strips, splits);
+#define SOWB_MMRK(RR)                                                                                     \
+  do {                                                                                                    \
+    auto k = tt_matmul_rk_reg_kernel<RR>;                                                                 \
+    constexpr size_t smem = size_t(1024) * RR;                                                            \
+    SOWB_CHECK_CUDA(set_max_smem_once(k, smem));                                                          \
+    SOWB_CHECK_CUDA(launch_pdl(k, rgrid, dim3(256), smem, stream, A, B, r, C, m, n, per));                \
+    return SOWB_OK;                                                                                       \
+  } while (0)
+    if (r <= 8) SOWB_MMRK(8);
+    if (r <= 16) SOWB_MMRK(16);
+    if (r <= 32) SOWB_MMRK(32);
+    SOWB_MMRK(64);
+#undef SOWB_MMRK
+  }
   dim3 grid(ceil_div(n, kRkTile), ceil_div(m, kRkTile));
   SOWB_REQUIRE(grid.y <= 65535, "tt_matmul_rk: m too large");
   tt_matmul_rk_kernel<<<grid, 256, 0, stream>>>(A, B, C, m, n, r);
@@ -2351,6 +2608,114 @@ int tt_adam_interleaved(void* p, const void* g, float* m, float* v, int M, int N
   else
     return set_error(SOWB_EINVAL, "tt_adam_interleaved: unknown dtype %d", dtype);
   SOWB_CHECK_CUDA(cudaGetLastError());
+  return SOWB_OK;
+}
+
+// ---- the whole TT-Adam step of an order >= 3 tensor train in one call ---------------------------------------------------
+// Host-side composition of the kernels above (no new device code): per moment the reconstruction chain into the interleaved
+// dense layout, one interleaved Adam pass over p / g / m / v, then ONE left-to-right sweep that decomposes both moments as a
+// batch of two (thin QR + projection per core).  Replaces ~25 separate C-ABI calls issued from Python, which is what bounded
+// the step (0.47 ms of host time per 4096 x 4096 order-3 parameter).
+struct AdamNPlan {
+  int64_t P, T;                 // P = mm * nn, T = P^order
+  size_t dense_off, buf_off[2], buf_bytes, qr_off, qr_bytes, pj_off, pj_bytes, total;
+  bool ok;
+};
+
+static AdamNPlan adamN_plan(int mm, int nn, int order, const int* ranks) {
+  AdamNPlan pl{};
+  pl.ok = false;
+  if (order < 3 || order > 8 || mm <= 0 || nn <= 0 || ranks == nullptr || ranks[0] != 1 || ranks[order] != 1) return pl;
+  pl.P = int64_t(mm) * nn;
+  pl.T = 1;
+  for (int k = 0; k < order; ++k) {
+    pl.T *= pl.P;
+    if (pl.T > (int64_t(1) << 34)) return pl;
+  }
+  int64_t cols = pl.T, buf_elems = 0;
+  for (int k = 0; k + 1 < order; ++k) {
+    const int64_t rows = int64_t(ranks[k]) * pl.P;
+    cols /= pl.P;                                           // columns of the unfolding at core k: P^(order-1-k)
+    const int r = ranks[k + 1];
+    if (r <= 0 || r > kCqMaxR || r > rows || r > cols || rows > 2147483647 || cols > 2147483647) return pl;
+    buf_elems = std::max(buf_elems, int64_t(r) * cols);     // R of the sweep == intermediate of the reconstruction chain
+    pl.qr_bytes = std::max(pl.qr_bytes, sow_thin_qr_workspace_bytes(int(rows), r, 2));
+    pl.pj_bytes = std::max(pl.pj_bytes, tt_project_workspace_bytes(int(rows), int(cols), r, 2));
+  }
+  auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+  pl.buf_bytes = up(size_t(2) * buf_elems * sizeof(float));
+  pl.dense_off = 0;
+  pl.buf_off[0] = up(size_t(2) * pl.T * sizeof(float));
+  pl.buf_off[1] = pl.buf_off[0] + pl.buf_bytes;
+  pl.qr_off = pl.buf_off[1] + pl.buf_bytes;
+  pl.qr_bytes = up(pl.qr_bytes);
+  pl.pj_off = pl.qr_off + pl.qr_bytes;
+  pl.total = pl.pj_off + up(pl.pj_bytes);
+  pl.ok = true;
+  return pl;
+}
+
+size_t tt_adam_nd_workspace_bytes(int mm, int nn, int order, const int* ranks) {
+  const AdamNPlan pl = adamN_plan(mm, nn, order, ranks);
+  return pl.ok ? pl.total : 0;
+}
+
+int tt_adam_nd_step(void* p, const void* g, const float* const* cores_in, float* const* cores_out, const int* ranks, int M, int N,
+                  int mm, int nn, int order, double beta1, double beta2, double eps, double step_size, double lr_wd,
+                  int first_step, int dtype, void* ws, size_t ws_bytes, void* stream_) {
+  SOWB_REQUIRE(p && g && cores_out && ranks && ws, "tt_adam_nd_step: null pointer argument");
+  SOWB_REQUIRE(first_step || cores_in, "tt_adam_nd_step: null core table");
+  const AdamNPlan pl = adamN_plan(mm, nn, order, ranks);
+  SOWB_REQUIRE(pl.ok, "tt_adam_nd_step: unsupported order / ranks (order 3..8, boundary ranks 1, inner ranks <= 64 and <= the unfolding sizes)");
+  SOWB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "tt_adam_nd_step: workspace must be 256-byte aligned");
+  if (ws_bytes < pl.total)
+    return set_error(SOWB_EWORKSPACE, "tt_adam_nd_step: workspace %zu B < required %zu B (tt_adam_nd_workspace_bytes)", ws_bytes, pl.total);
+  if (int rc0 = ensure_context_for(g)) return rc0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  float* dense = reinterpret_cast<float*>(w + pl.dense_off);           // [2][T]: m, v in the interleaved layout
+  float* buf[2] = {reinterpret_cast<float*>(w + pl.buf_off[0]), reinterpret_cast<float*>(w + pl.buf_off[1])};
+  const int64_t P = pl.P, T = pl.T;
+  int rc;
+  // 1. old moments: reconstruction chain per moment (tt.py:213-237), or zeros on the first step (ttadam.py:68-70,76-78)
+  if (first_step) {
+    SOWB_CHECK_CUDA(cudaMemsetAsync(dense, 0, size_t(2) * T * sizeof(float), stream));
+  } else {
+    for (int b = 0; b < 2; ++b) {
+      const float* res = cores_in[0] + int64_t(b) * ranks[0] * P * ranks[1];     // [P, r_1]
+      int64_t rows = P;
+      for (int k = 1; k < order; ++k) {
+        const float* core = cores_in[k] + int64_t(b) * ranks[k] * P * ranks[k + 1];   // [r_k, P * r_{k+1}]
+        float* out = (k == order - 1) ? dense + int64_t(b) * T : buf[k & 1];
+        const int64_t n = P * ranks[k + 1];
+        SOWB_REQUIRE(rows <= 2147483647 && n <= 2147483647, "tt_adam_nd_step: unfolding too large");
+        rc = tt_matmul_rk(res, core, out, int(rows), int(n), ranks[k], stream_);
+        if (rc) return rc;
+        res = out;
+        rows *= P;                                                               // [rows, P * r] viewed as [rows * P, r]
+      }
+    }
+  }
+  // 2. Adam on p, new moments in place (interleaved layout, zero at padded positions)
+  rc = tt_adam_interleaved(p, g, dense, dense + T, M, N, mm, nn, order, beta1, beta2, eps, step_size, lr_wd, dtype, stream_);
+  if (rc) return rc;
+  // 3. decomposition sweep, both moments as a batch of two (tt.py:111-140)
+  const float* cur = dense;
+  int64_t cur_bs = T, cols = T;
+  for (int k = 0; k + 1 < order; ++k) {
+    const int64_t rows = int64_t(ranks[k]) * P;
+    cols /= P;
+    const int r = ranks[k + 1];
+    float* Qk = cores_out[k];                                                    // [2][rows, r]
+    rc = sow_thin_qr(cur, cur_bs, int(cols), Qk, rows * r, int(rows), r, 2, w + pl.qr_off, pl.qr_bytes, stream_);
+    if (rc) return rc;
+    const bool last = (k + 2 == order);
+    float* Rk = last ? cores_out[order - 1] : buf[k & 1];                        // [2][r, cols]
+    rc = tt_project(cur, cur_bs, Qk, rows * r, Rk, int64_t(r) * cols, int(rows), int(cols), r, 2, w + pl.pj_off, pl.pj_bytes, stream_);
+    if (rc) return rc;
+    cur = Rk;
+    cur_bs = int64_t(r) * cols;
+  }
   return SOWB_OK;
 }
 

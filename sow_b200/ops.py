@@ -464,6 +464,49 @@ class TTAdam2Plan:
         return out
 
 
+class TTAdamNPlan:
+    """Persistent state of the one-call TT-Adam step of ONE parameter with an order >= 3 tensor train (tt_adam_nd_step):
+    two sets of cores used ping-pong, the k-th core of both moments in one (2, r_k * P * r_{k+1}) tensor, and the pointer
+    tables of both sets.  ``supported`` is False when the C entry point does not take the shape (a rank above 64 or above
+    an unfolding size): the caller then keeps the op-by-op path."""
+
+    def __init__(self, device, mm: int, nn: int, ranks):
+        lib = _lib.load()
+        self.mm, self.nn, self.ranks, self.order = mm, nn, [int(r) for r in ranks], len(ranks) - 1
+        self.P = mm * nn
+        self._ranks_c = (ctypes.c_int * len(self.ranks))(*self.ranks)
+        self.ws_bytes = lib.tt_adam_nd_workspace_bytes(mm, nn, self.order, self._ranks_c)
+        self.supported = self.ws_bytes > 0
+        self.device = device
+        self.cur = -1
+        if not self.supported:
+            return
+        P, rk = self.P, self.ranks
+        self.bufs = [[torch.empty((2, rk[k] * P * rk[k + 1]), dtype=torch.float32, device=device) for k in range(self.order)]
+                     for _ in range(2)]
+        self._tab = [(ctypes.c_void_p * self.order)(*[t.data_ptr() for t in self.bufs[s]]) for s in range(2)]
+
+    def cores(self, s: int, b: int):
+        """Cores (r_k, mm, nn, r_{k+1}) of moment b (0: m, 1: v) in set s, as views."""
+        rk = self.ranks
+        return [self.bufs[s][k][b].reshape(rk[k], self.mm, self.nn, rk[k + 1]) for k in range(self.order)]
+
+    def step(self, p, g, beta1, beta2, eps, step_size, lr_wd) -> int:
+        lib = _lib.load()
+        first = self.cur < 0
+        out = 0 if first else 1 - self.cur
+        M, N = p.shape
+        ws = workspace(self.device, self.ws_bytes)
+        rc = lib.tt_adam_nd_step(_p(p), _p(g), None if first else self._tab[self.cur], self._tab[out], self._ranks_c, M, N,
+                               self.mm, self.nn, self.order, float(beta1), float(beta2), float(eps), float(step_size),
+                               float(lr_wd), 1 if first else 0, _dtype_code(p.dtype), _p(ws), ws.numel(),
+                               _stream_ptr(self.device))
+        check(rc, "tt_adam_nd_step")
+        launch_counter["kernels"] += 2 * (self.order - 1) + 1 + 8 * (self.order - 1)
+        self.cur = out
+        return out
+
+
 def tt_adam_interleaved(p, g, m, v, mm, nn, order, beta1, beta2, eps, step_size, lr_wd):
     """In-place TT-Adam on interleaved fp32 moments m, v ((mm*nn)^order elements each); p, g are (M,N)."""
     _require_cuda(p, g, m, v)

@@ -150,8 +150,40 @@ class TTAdam(torch.optim.Optimizer):
                 tt.cores = [Q[b].reshape(1, mm, nn_, r), R[b].reshape(r, mm, nn_, 1)]
                 state[key] = tt
             return
-        # order > 2: the moments stay in the interleaved layout between the reconstruction chain, the Adam kernel and the
-        # decomposition sweep (no de-interleave / interleave passes; ttadam.py:71-84,113-115)
+        if order > 2 and g.is_contiguous():
+            # the whole step as one C-ABI call (reconstruction chains, interleaved Adam, one batched decomposition sweep)
+            # through a per-parameter plan, like the order-2 path above
+            nplans = plans.setdefault("_order_n", {})
+            plan = nplans.get(p)
+            if plan is not None and first:
+                plan.cur = -1
+            if plan is None or (plan.mm, plan.nn, plan.ranks) != (mm, nn_, [int(r) for r in ranks]):
+                plan = ops.TTAdamNPlan(pd.device, mm, nn_, ranks)
+                nplans[p] = plan
+                if plan.supported:
+                    plan.tts = []
+                    for s_ in range(2):
+                        pair = []
+                        for b in range(2):
+                            tt = TensorTrain(list(ranks), (mm,) * order, (nn_,) * order, device=pd.device)
+                            tt.cores = plan.cores(s_, b)
+                            pair.append(tt)
+                        plan.tts.append(pair)
+            if plan.supported:
+                live = (not first and plan.cur >= 0 and state["exp_avg"] is plan.tts[plan.cur][0]
+                        and state["exp_avg_sq"] is plan.tts[plan.cur][1])
+                if not first and not live:
+                    # moments that did not come from this plan (loaded checkpoint, replaced by the caller): copy them in
+                    for b, key in enumerate(("exp_avg", "exp_avg_sq")):
+                        for k in range(order):
+                            plan.bufs[0][k][b].copy_(state[key].cores[k].reshape(-1))
+                    plan.cur = 0
+                k_out = plan.step(pd, g, beta1, beta2, eps, step_size, lr_wd)
+                state["exp_avg"], state["exp_avg_sq"] = plan.tts[k_out]
+                return
+        # order > 2, op by op (ranks the one-call path does not take): the moments stay in the interleaved layout between the
+        # reconstruction chain, the Adam kernel and the decomposition sweep (no de-interleave / interleave passes;
+        # ttadam.py:71-84,113-115)
         total = (mm * nn_) ** order
         if first:
             m = torch.zeros((total,), dtype=torch.float32, device=pd.device)

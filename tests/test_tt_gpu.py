@@ -208,19 +208,21 @@ def test_decompose_is_bit_reproducible():
             assert torch.equal(a, b)
 
 
-def test_ttadam_plan_survives_replaced_and_reset_state(golden_tt):
-    """The fused order-2 path keeps persistent core buffers per parameter.  Moments that were replaced behind its back (a
+@pytest.mark.parametrize("case", ["o2", "o3"])
+def test_ttadam_plan_survives_replaced_and_reset_state(golden_tt, case):
+    """The one-call paths (order 2 and order >= 3) keep persistent core buffers per parameter.  Moments that were replaced behind its back (a
     loaded checkpoint) must be picked up, and a cleared state must restart from zero moments: both runs reproduce the
     uninterrupted trajectory bit for bit."""
     from tn_gradient.optimizer.ttadam import TTAdam
     from tn_gradient.tt import TensorTrain
     g = golden_tt
-    grads = [torch.from_numpy(x).cuda() for x in g["ttadam/o2/grads"]]
-    ranks = [int(r) for r in g["ttadam/o2/ranks"]]
+    grads = [torch.from_numpy(x).cuda() for x in g[f"ttadam/{case}/grads"]]
+    ranks = [int(r) for r in g[f"ttadam/{case}/ranks"]]
+    wd = float(g[f"ttadam/{case}/wd"])
 
     def run(interfere):
-        p = torch.nn.Parameter(torch.from_numpy(g["ttadam/o2/p0"]).cuda())
-        opt = TTAdam([{"params": [p], "ranks": list(ranks)}], lr=1e-2)
+        p = torch.nn.Parameter(torch.from_numpy(g[f"ttadam/{case}/p0"]).cuda())
+        opt = TTAdam([{"params": [p], "ranks": list(ranks)}], lr=1e-2, weight_decay=wd)
         for step, grad in enumerate(grads):
             p.grad = grad
             opt.step()
@@ -235,16 +237,16 @@ def test_ttadam_plan_survives_replaced_and_reset_state(golden_tt):
     assert torch.equal(p_ref, p_int)
     for a, b in zip(cores_ref, cores_int):
         assert torch.equal(a, b)
-    assert rel_err(p_ref.cpu().numpy(), g["ttadam/o2/p5"]) < 2e-5
+    assert rel_err(p_ref.cpu().numpy(), g[f"ttadam/{case}/p5"]) < 2e-5
 
     # reset: clearing the state restarts from zero moments (the plan's stale cores must not leak in)
-    p = torch.nn.Parameter(torch.from_numpy(g["ttadam/o2/p0"]).cuda())
-    opt = TTAdam([{"params": [p], "ranks": list(ranks)}], lr=1e-2)
+    p = torch.nn.Parameter(torch.from_numpy(g[f"ttadam/{case}/p0"]).cuda())
+    opt = TTAdam([{"params": [p], "ranks": list(ranks)}], lr=1e-2, weight_decay=wd)
     p.grad = grads[0]
     opt.step()
     p1 = p.detach().clone()
     opt.state[p].clear()
     with torch.no_grad():
-        p.copy_(torch.from_numpy(g["ttadam/o2/p0"]).cuda())
+        p.copy_(torch.from_numpy(g[f"ttadam/{case}/p0"]).cuda())
     opt.step()
     assert torch.equal(p.detach(), p1)
