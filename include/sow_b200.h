@@ -259,6 +259,18 @@ int tt_adam_nd_step(void* p, const void* g, const float* const* cores_in, float*
                   int mm, int nn, int order, double beta1, double beta2, double eps, double step_size, double lr_wd,
                   int first_step, int dtype, void* ws, size_t ws_bytes, void* stream);
 
+/*
+ * TensorTrain.from_matrix / to_matrix of an order >= 3 tensor train as ONE call each (tt.py:48-67,111-140 / 213-247):
+ * tt_interleave + the thin-QR / projection sweep, and the reconstruction chain + tt_deinterleave.  cores[k]: the k-th core,
+ * r_k * P * r_{k+1} fp32, P = mm*nn; ranks as in tt_adam_nd_step.  ws: tt_nd_workspace_bytes(...) (0 = unsupported), 256-byte
+ * aligned.  src / dst: (M, N) row-major of dtype `dtype`.
+ */
+size_t tt_nd_workspace_bytes(int mm, int nn, int order, const int* ranks);
+int tt_decompose_nd(const void* src, float* const* cores_out, const int* ranks, int M, int N, int mm, int nn, int order, int dtype,
+                    void* ws, size_t ws_bytes, void* stream);
+int tt_reconstruct_nd(const float* const* cores, const int* ranks, void* dst, int M, int N, int mm, int nn, int order, int dtype,
+                      void* ws, size_t ws_bytes, void* stream);
+
 /* Same update on dense fp32 moments m, v of shape (M,N) (no "ranks": the dense branch); v is clamped at 0 first (ttadam.py:84). */
 int tt_adam_dense(void* p, const void* g, float* m, float* v, int64_t numel, double beta1, double beta2, double eps,
                   double step_size, double lr_wd, int dtype, void* stream);

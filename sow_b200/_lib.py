@@ -93,6 +93,9 @@ SIGNATURES = {
     "tt_adam2_fused_workspace_bytes": (_sz, [_i, _i]),
     "tt_adam2_workspace_bytes": (_sz, [_i, _i]),
     "tt_adam_nd_workspace_bytes": (_sz, [_i, _i, _i, _vp]),
+    "tt_nd_workspace_bytes": (_sz, [_i, _i, _i, _vp]),
+    "tt_decompose_nd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "tt_reconstruct_nd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "tt_adam_nd_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i, _vp, _sz, _vp]),
     "tt_adam2_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _i,
                            _vp, _sz, _vp]),

@@ -2622,7 +2622,7 @@ struct AdamNPlan {
   bool ok;
 };
 
-static AdamNPlan adamN_plan(int mm, int nn, int order, const int* ranks) {
+static AdamNPlan adamN_plan(int mm, int nn, int order, const int* ranks, int batch = 2) {
   AdamNPlan pl{};
   pl.ok = false;
   if (order < 3 || order > 8 || mm <= 0 || nn <= 0 || ranks == nullptr || ranks[0] != 1 || ranks[order] != 1) return pl;
@@ -2639,13 +2639,13 @@ static AdamNPlan adamN_plan(int mm, int nn, int order, const int* ranks) {
     const int r = ranks[k + 1];
     if (r <= 0 || r > kCqMaxR || r > rows || r > cols || rows > 2147483647 || cols > 2147483647) return pl;
     buf_elems = std::max(buf_elems, int64_t(r) * cols);     // R of the sweep == intermediate of the reconstruction chain
-    pl.qr_bytes = std::max(pl.qr_bytes, sow_thin_qr_workspace_bytes(int(rows), r, 2));
-    pl.pj_bytes = std::max(pl.pj_bytes, tt_project_workspace_bytes(int(rows), int(cols), r, 2));
+    pl.qr_bytes = std::max(pl.qr_bytes, sow_thin_qr_workspace_bytes(int(rows), r, batch));
+    pl.pj_bytes = std::max(pl.pj_bytes, tt_project_workspace_bytes(int(rows), int(cols), r, batch));
   }
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-  pl.buf_bytes = up(size_t(2) * buf_elems * sizeof(float));
+  pl.buf_bytes = up(size_t(batch) * buf_elems * sizeof(float));
   pl.dense_off = 0;
-  pl.buf_off[0] = up(size_t(2) * pl.T * sizeof(float));
+  pl.buf_off[0] = up(size_t(batch) * pl.T * sizeof(float));
   pl.buf_off[1] = pl.buf_off[0] + pl.buf_bytes;
   pl.qr_off = pl.buf_off[1] + pl.buf_bytes;
   pl.qr_bytes = up(pl.qr_bytes);
@@ -2717,6 +2717,66 @@ int tt_adam_nd_step(void* p, const void* g, const float* const* cores_in, float*
     cur_bs = int64_t(r) * cols;
   }
   return SOWB_OK;
+}
+
+// from_matrix / to_matrix of an order >= 3 tensor train as one call each (same composition, one matrix instead of two moments)
+size_t tt_nd_workspace_bytes(int mm, int nn, int order, const int* ranks) {
+  const AdamNPlan pl = adamN_plan(mm, nn, order, ranks, 1);
+  return pl.ok ? pl.total : 0;
+}
+
+int tt_decompose_nd(const void* src, float* const* cores_out, const int* ranks, int M, int N, int mm, int nn, int order, int dtype,
+                    void* ws, size_t ws_bytes, void* stream_) {
+  SOWB_REQUIRE(src && cores_out && ranks && ws, "tt_decompose_nd: null pointer argument");
+  const AdamNPlan pl = adamN_plan(mm, nn, order, ranks, 1);
+  SOWB_REQUIRE(pl.ok, "tt_decompose_nd: unsupported order / ranks");
+  SOWB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "tt_decompose_nd: workspace must be 256-byte aligned");
+  if (ws_bytes < pl.total)
+    return set_error(SOWB_EWORKSPACE, "tt_decompose_nd: workspace %zu B < required %zu B (tt_nd_workspace_bytes)", ws_bytes, pl.total);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  float* dense = reinterpret_cast<float*>(w + pl.dense_off);
+  float* buf[2] = {reinterpret_cast<float*>(w + pl.buf_off[0]), reinterpret_cast<float*>(w + pl.buf_off[1])};
+  int rc = tt_interleave(src, M, N, mm, nn, order, dense, dtype, stream_);
+  if (rc) return rc;
+  const float* cur = dense;
+  int64_t cols = pl.T;
+  for (int k = 0; k + 1 < order; ++k) {
+    const int64_t rows = int64_t(ranks[k]) * pl.P;
+    cols /= pl.P;
+    const int r = ranks[k + 1];
+    rc = sow_thin_qr(cur, 0, int(cols), cores_out[k], 0, int(rows), r, 1, w + pl.qr_off, pl.qr_bytes, stream_);
+    if (rc) return rc;
+    float* Rk = (k + 2 == order) ? cores_out[order - 1] : buf[k & 1];
+    rc = tt_project(cur, 0, cores_out[k], 0, Rk, 0, int(rows), int(cols), r, 1, w + pl.pj_off, pl.pj_bytes, stream_);
+    if (rc) return rc;
+    cur = Rk;
+  }
+  return SOWB_OK;
+}
+
+int tt_reconstruct_nd(const float* const* cores, const int* ranks, void* dst, int M, int N, int mm, int nn, int order, int dtype,
+                      void* ws, size_t ws_bytes, void* stream_) {
+  SOWB_REQUIRE(cores && ranks && dst && ws, "tt_reconstruct_nd: null pointer argument");
+  const AdamNPlan pl = adamN_plan(mm, nn, order, ranks, 1);
+  SOWB_REQUIRE(pl.ok, "tt_reconstruct_nd: unsupported order / ranks");
+  SOWB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "tt_reconstruct_nd: workspace must be 256-byte aligned");
+  if (ws_bytes < pl.total)
+    return set_error(SOWB_EWORKSPACE, "tt_reconstruct_nd: workspace %zu B < required %zu B (tt_nd_workspace_bytes)", ws_bytes, pl.total);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  float* dense = reinterpret_cast<float*>(w + pl.dense_off);
+  float* buf[2] = {reinterpret_cast<float*>(w + pl.buf_off[0]), reinterpret_cast<float*>(w + pl.buf_off[1])};
+  const float* res = cores[0];
+  int64_t rows = pl.P;
+  for (int k = 1; k < order; ++k) {
+    float* out = (k == order - 1) ? dense : buf[k & 1];
+    const int64_t n = pl.P * ranks[k + 1];
+    SOWB_REQUIRE(rows <= 2147483647 && n <= 2147483647, "tt_reconstruct_nd: unfolding too large");
+    const int rc = tt_matmul_rk(res, cores[k], out, int(rows), int(n), ranks[k], stream_);
+    if (rc) return rc;
+    res = out;
+    rows *= pl.P;
+  }
+  return tt_deinterleave(dense, M, N, mm, nn, order, dst, dtype, stream_);
 }
 
 int tt_adam_dense(void* p, const void* g, float* m, float* v, int64_t numel, double beta1_d, double beta2_d,

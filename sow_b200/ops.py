@@ -464,6 +464,51 @@ class TTAdam2Plan:
         return out
 
 
+def decompose_nd(src: torch.Tensor, mm: int, nn: int, ranks):
+    """Order >= 3 TT of a (M,N) bf16/fp32 matrix in one C-ABI call (tt_decompose_nd).  Returns the cores as
+    (r_k, mm, nn, r_{k+1}) fp32 tensors, or None when the entry point does not take the ranks (caller: op-by-op sweep)."""
+    _require_cuda(src)
+    lib = _lib.load()
+    ranks = [int(r) for r in ranks]
+    order = len(ranks) - 1
+    ranks_c = (ctypes.c_int * len(ranks))(*ranks)
+    ws_bytes = lib.tt_nd_workspace_bytes(mm, nn, order, ranks_c)
+    if ws_bytes == 0:
+        return None
+    src = src.contiguous()
+    M, N = src.shape
+    P = mm * nn
+    cores = [torch.empty((ranks[k], mm, nn, ranks[k + 1]), dtype=torch.float32, device=src.device) for k in range(order)]
+    tab = (ctypes.c_void_p * order)(*[c.data_ptr() for c in cores])
+    ws = workspace(src.device, ws_bytes)
+    rc = lib.tt_decompose_nd(_p(src), tab, ranks_c, M, N, mm, nn, order, _dtype_code(src.dtype), _p(ws), ws.numel(),
+                             _stream_ptr(src.device))
+    check(rc, "tt_decompose_nd")
+    launch_counter["kernels"] += 1 + 5 * (order - 1)
+    return cores
+
+
+def reconstruct_nd(cores, M: int, N: int, mm: int, nn: int, dtype=torch.float32):
+    """(M,N) window of an order >= 3 TT in one C-ABI call (tt_reconstruct_nd); None when the ranks are not supported."""
+    lib = _lib.load()
+    order = len(cores)
+    ranks = [int(c.shape[0]) for c in cores] + [int(cores[-1].shape[-1])]
+    ranks_c = (ctypes.c_int * len(ranks))(*ranks)
+    ws_bytes = lib.tt_nd_workspace_bytes(mm, nn, order, ranks_c)
+    if ws_bytes == 0:
+        return None
+    cs = [c.detach().to(torch.float32).contiguous() for c in cores]
+    _require_cuda(*cs)
+    dev = cs[0].device
+    out = torch.empty((M, N), dtype=dtype, device=dev)
+    tab = (ctypes.c_void_p * order)(*[c.data_ptr() for c in cs])
+    ws = workspace(dev, ws_bytes)
+    rc = lib.tt_reconstruct_nd(tab, ranks_c, _p(out), M, N, mm, nn, order, _dtype_code(dtype), _p(ws), ws.numel(), _stream_ptr(dev))
+    check(rc, "tt_reconstruct_nd")
+    launch_counter["kernels"] += order
+    return out
+
+
 class TTAdamNPlan:
     """Persistent state of the one-call TT-Adam step of ONE parameter with an order >= 3 tensor train (tt_adam_nd_step):
     two sets of cores used ping-pong, the k-th core of both moments in one (2, r_k * P * r_{k+1}) tensor, and the pointer

@@ -130,6 +130,11 @@ class TensorTrain:
             tt.cores = [Q.reshape(1, mm, nn_, r), R.reshape(r, mm, nn_, 1)]
             tt.device = matrix.device
             return tt
+        cores = ops.decompose_nd(src, mm, nn_, ranks)          # interleave + sweep in one C-ABI call (inner ranks <= 64)
+        if cores is not None:
+            tt.cores = cores
+            tt.device = matrix.device
+            return tt
         flat = ops.interleave(src, mm, nn_, order)
         tt._decompose_interleaved(flat)
         return tt.to(matrix.device)
@@ -235,6 +240,10 @@ class TensorTrain:
             return ops.reconstruct2(G1, G2, min(int(shape[0]), mm * mm), min(int(shape[1]), nn_ * nn_), mm, nn_)
         if _uniform(self.input_shape) and _uniform(self.output_shape) and self.cores[0].is_cuda:
             # fused de-interleave + unpad: only the (M, N) window is written
+            mm, nn_ = int(self.input_shape[0]), int(self.output_shape[0])
+            out = ops.reconstruct_nd(self.cores, min(int(shape[0]), mm ** d), min(int(shape[1]), nn_ ** d), mm, nn_)
+            if out is not None:
+                return out
             c0 = self.cores[0]
             res = c0.detach().to(torch.float32).reshape(-1, c0.shape[-1])
             for c in self.cores[1:]:
