@@ -1209,6 +1209,9 @@ tt_adam2_kernel(T* __restrict__ p, const T* __restrict__ g, const float* __restr
 //   -> 2 . R . CT = 64 accumulators per thread in every configuration; tile = 32 rows x 64 columns.
 // G1 / Q' tiles are staged by cp.async, three buffers deep (one barrier per tile); g and p of the tile are requested
 // before the barrier and consumed after the reconstruction FMAs.
+// Measured and dropped: serving rows whose offset is not a multiple of four elements (4096 x 11008: nn = 105, three rows in
+// four) with two aligned halves or element / pair / element instead of four element accesses -- 0.38 -> 0.51 ms per step at
+// r = 8 (a third raw register per row and a three-way unpack / store per row cost more than the saved accesses).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CT>
 struct RawVec;

@@ -10,8 +10,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sow_b200 import _lib, ops  # noqa: E402
 from tn_gradient.optimizer.ttadam import TTAdam  # noqa: E402
 
-M = N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-r = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+if len(sys.argv) > 3:                      # M N r
+    M, N, r = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+else:                                      # M r (square)
+    M = N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    r = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 dev = torch.device("cuda", 0)
 p = torch.nn.Parameter((torch.randn(M, N, device=dev) * 0.02).bfloat16())
 p.grad = (torch.randn(M, N, device=dev) * 0.01).bfloat16()
@@ -34,7 +37,8 @@ def bench(fn, n=300):
 
 print("opt.step            : host %.1f us/step, with final sync %.1f us/step" % bench(opt.step))
 st = opt.state[p]
-mm = nn_ = int(round(M ** 0.5))
+from math import ceil
+mm, nn_ = ceil(M ** 0.5), ceil(N ** 0.5)
 P = mm * nn_
 tm, tv = st["exp_avg"], st["exp_avg_sq"]
 cm = (tm.cores[0].reshape(P, -1).contiguous(), tm.cores[1].reshape(-1, P).contiguous())
