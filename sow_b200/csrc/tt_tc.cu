@@ -180,7 +180,8 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
   uint64_t* bar_ld = bars;        // TMA: core pieces landed
   uint64_t* bar_q = bars + 1;     // TMA: Q' pieces landed
   uint64_t* bar_mma = bars + 2;   // UMMA batch complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bar_ld2 = bars + 3;   // TMA: second moment's core pieces landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = prm.P, nn = prm.nn, mm = prm.mm, M = prm.M, N = prm.N;
@@ -192,6 +193,7 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
     tma_prefetch_desc(&tmQm);
     tma_prefetch_desc(&tmQv);
     mbar_init(bar_ld, 1);
+    mbar_init(bar_ld2, 1);
     mbar_init(bar_q, 1);
     mbar_init(bar_mma, 1);
     fence_mbar_init();
@@ -292,25 +294,27 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
     // ---------------- 1. loads + reconstruction UMMAs (one thread) ----------------
     if (tid == 0) {
       if (!prm.first_step) {
-        // both moments' core pieces at once: m into the operand region, v into the (still idle) Q' region
-        mbar_expect_tx(bar_ld, 2 * kTcOpBytes);
+        // both moments' core pieces at once: m into the operand region, v into the (still idle) Q' region -- one barrier per
+        // moment, so that the reconstruction MMAs of m run while the pieces of v are still landing
+        mbar_expect_tx(bar_ld, kTcOpBytes);
+        mbar_expect_tx(bar_ld2, kTcOpBytes);
 #pragma unroll
         for (int mom = 0; mom < 2; ++mom) {
           const CUtensorMap* m1 = mom ? &tmG1v : &tmG1m;
           const CUtensorMap* m2 = mom ? &tmG2v : &tmG2m;
           uint8_t* base = mom ? sQ : sOp;
+          uint64_t* bar = mom ? bar_ld2 : bar_ld;
 #pragma unroll
           for (int pc = 0; pc < 3; ++pc) {
-            tma_load_2d(base + pc * 16384, m1, bar_ld, 0, pc * prm.P_pad + a0);
-            tma_load_2d(base + 49152 + pc * 16384, m2, bar_ld, b0, pc * 64);
-            tma_load_2d(base + 49152 + pc * 16384 + 8192, m2, bar_ld, b0 + 64, pc * 64);
+            tma_load_2d(base + pc * 16384, m1, bar, 0, pc * prm.P_pad + a0);
+            tma_load_2d(base + 49152 + pc * 16384, m2, bar, b0, pc * 64);
+            tma_load_2d(base + 49152 + pc * 16384 + 8192, m2, bar, b0 + 64, pc * 64);
           }
         }
-        mbar_wait(bar_ld, ph_ld);
-        ph_ld ^= 1;
-        tc_fence_after();
 #pragma unroll
         for (int mom = 0; mom < 2; ++mom) {
+          mbar_wait(mom ? bar_ld2 : bar_ld, ph_ld);
+          tc_fence_after();
           const uint32_t tS = mom ? tS_v : tS_m;
           const uint32_t ob = mom ? sQ_u : sOp_u;
           bool first = true;
@@ -327,6 +331,7 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
               }
             }
         }
+        ph_ld ^= 1;
         umma_commit(bar_mma);
         mbar_wait(bar_mma, ph_mma);     // both operand regions are overwritten next (m' pieces / Q' pieces)
         ph_mma ^= 1;
