@@ -63,6 +63,19 @@ __global__ void tt_split3_kernel(const __grid_constant__ SplitJobs jobs) {
   }
 }
 
+// MUFU square root / reciprocal (<= 2 ulp each): the update term is scaled by the step size before it meets p (same choice
+// and same trajectory bound as tt_adam2_reg_kernel)
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void split3(float x, uint16_t& b0, uint16_t& b1, uint16_t& b2) {
   const __nv_bfloat16 h0 = __float2bfloat16(x);
   x -= __bfloat162float(h0);
@@ -404,7 +417,7 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
               const float vo = prm.beta2 * vp + prm.omb2 * gv[e] * gv[e];                            // ttadam.py:93
               if (pass == 0) {
                 const float mo = prm.beta1 * mp + prm.omb1 * gv[e];                                  // ttadam.py:92
-                pv[e] -= prm.step_size * __fdividef(mo, sqrtf(vo) + prm.eps);                        // ttadam.py:94,103,108
+                pv[e] -= prm.step_size * mo * rcp_approx(sqrt_approx(vo) + prm.eps);                        // ttadam.py:94,103,108
                 if (prm.lr_wd > 0.f) pv[e] -= prm.lr_wd * pv[e];                                     // ttadam.py:110-111
                 split3(mo, b[0][e], b[1][e], b[2][e]);
               } else {
@@ -443,7 +456,7 @@ tt_adam2_tc_kernel(const __grid_constant__ CUtensorMap tmG1m, const __grid_const
                 vo = prm.beta2 * fmaxf(vp, 0.f) + prm.omb2 * gv * gv;
                 if (pass == 0) {
                   float pv = load1<T>(p, ee);
-                  pv -= prm.step_size * __fdividef(mo, sqrtf(vo) + prm.eps);
+                  pv -= prm.step_size * mo * rcp_approx(sqrt_approx(vo) + prm.eps);
                   if (prm.lr_wd > 0.f) pv -= prm.lr_wd * pv;
                   store1<T>(p, ee, pv);
                 }
