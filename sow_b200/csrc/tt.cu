@@ -159,7 +159,9 @@ thin_qr_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __rest
 constexpr int kCqMaxR = 64;
 constexpr int kCqRows = 128;
 constexpr int kCqGramRows = 64;    // rows per Gram block: the fp64 pipe is narrow, so the work is spread over more SMs
-constexpr size_t kCqWsPerBatch = (kCqMaxR * kCqMaxR + kCqMaxR) * sizeof(double);
+// per-matrix factor block: L (64 x 64, lower) | dinv (64) | W = L^-T (64 x 64, upper: the operand of the tensor-core solve)
+constexpr int kCqFac = 2 * kCqMaxR * kCqMaxR + kCqMaxR;
+constexpr size_t kCqWsPerBatch = kCqFac * sizeof(double);
 
 // Gram partials: CTA (x, b) accumulates X_b[rows]^T X_b[rows] in fp64 over the 128-row blocks x, x + gridDim.x, ... (fixed
 // order) and stores the lower triangle compactly, part[(b * gridDim.x + x)][i * r + j].  cq_sum_kernel adds the
@@ -235,7 +237,7 @@ cq_sum_kernel(const double* __restrict__ part, int n_part, int r, double* __rest
     for (int u = 0; u < 8; ++u) g += v[u];
   }
   for (; q < n_part; ++q) g += pp[static_cast<int64_t>(q) * rr];
-  ws[blockIdx.y * (kCqMaxR * kCqMaxR + kCqMaxR) + i * kCqMaxR + j] = g;
+  ws[blockIdx.y * kCqFac + i * kCqMaxR + j] = g;
 }
 
 // In place: lower triangle of G -> L; dinv[j] = 1 / L_jj (0 for a dependent column).  1024 threads, 4 entries each.
@@ -243,14 +245,16 @@ cq_sum_kernel(const double* __restrict__ part, int n_part, int r, double* __rest
 // column j, A[i][k] -= A[i][j] A[k][j] / d_j, so there is ONE barrier per step; L = A . diag(d)^-1/2 at the end.
 __global__ void __launch_bounds__(1024)
 cq_chol_kernel(double* __restrict__ ws, const double* __restrict__ part, int n_part, int r, int* __restrict__ flags,
-               const int* __restrict__ only_if) {
+               const int* __restrict__ only_if, int want_inv) {
   pdl_trigger();
   pdl_wait();
   if (only_if != nullptr && only_if[blockIdx.x] == 0) return;
-  __shared__ double A[kCqMaxR][kCqMaxR + 1];
-  __shared__ double g0[kCqMaxR];
-  __shared__ double dfin[kCqMaxR];      // final pivots (0 for a dependent column)
-  double* G = ws + blockIdx.x * (kCqMaxR * kCqMaxR + kCqMaxR);
+  extern __shared__ __align__(16) double chol_smem[];
+  double (*A)[kCqMaxR + 1] = reinterpret_cast<double (*)[kCqMaxR + 1]>(chol_smem);
+  double (*Li)[kCqMaxR + 1] = A + kCqMaxR;                          // L^-1 (want_inv)
+  double* g0 = reinterpret_cast<double*>(Li + kCqMaxR);
+  double* dfin = g0 + kCqMaxR;          // final pivots (0 for a dependent column)
+  double* G = ws + blockIdx.x * kCqFac;
   double* dinv = G + kCqMaxR * kCqMaxR;
   const int tid = threadIdx.x;
   const int i = tid >> 4, kb = tid & 15;
@@ -305,14 +309,173 @@ cq_chol_kernel(double* __restrict__ ws, const double* __restrict__ part, int n_p
     if (i < r && k <= i) {
       const double d = dfin[k];
       const double s = d > 0.0 ? rsqrt(d) : 0.0;
-      G[i * kCqMaxR + k] = (k == i) ? (d > 0.0 ? sqrt(d) : 1.0) : A[i][k] * s;   // dependent column: L_jj = 1, rest 0
+      const double lv = (k == i) ? (d > 0.0 ? sqrt(d) : 1.0) : A[i][k] * s;      // dependent column: L_jj = 1, rest 0
+      G[i * kCqMaxR + k] = lv;
+      A[i][k] = lv;                                                               // own entry: L stays in smem for the inverse
     }
   }
   if (tid < r) {
     const double d = dfin[tid];
-    dinv[tid] = d > 0.0 ? rsqrt(d) : 0.0;
+    const double di = d > 0.0 ? rsqrt(d) : 0.0;
+    dinv[tid] = di;
+    g0[tid] = di;                                                                 // g0 is dead: dinv for the inverse below
   }
   if (tid == 0 && flags != nullptr) flags[blockIdx.x] = weak ? 1 : 0;
+  if (!want_inv) return;
+  // The tensor-core solve is a forward substitution blocked by 8 columns: it needs L and the inverses of the eight 8 x 8
+  // diagonal blocks of L only (an explicit 64 x 64 inverse is a 64-step chain of dependent fp64 operations: 30 us).
+  // Thread (b, c), tid < 64: column c of inv(L_bb), eight unrolled steps; stored transposed as W[8b + c][8b + j], j >= c.
+  __syncthreads();
+  if (tid < kCqMaxR) {
+    const int b8 = (tid >> 3) * 8, c = tid & 7;
+    double y[8];
+#pragma unroll
+    for (int i2 = 0; i2 < 8; ++i2) {
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k >= c && k < i2) sum = fma(A[b8 + i2][b8 + k], y[k], sum);
+      y[i2] = (i2 < c) ? 0.0 : (i2 == c ? g0[b8 + c] : -sum * g0[b8 + i2]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Li[b8 + c][b8 + j] = y[j];          // Li[k][j] = inv(L_bb)[j][k]: already transposed
+  }
+  __syncthreads();
+  double* Wg = G + kCqMaxR * kCqMaxR + kCqMaxR;
+  for (int idx = tid; idx < kCqMaxR * kCqMaxR; idx += 1024) {
+    const int k = idx >> 6, j = idx & 63;
+    Wg[idx] = ((k >> 3) == (j >> 3) && k <= j && j < r) ? Li[k][j] : 0.0;
+  }
+}
+
+// ---- tensor-core (fp64 mma.sync m8n8k4) Gram and solve for ranks above 16 ------------------------------------------------
+// The CUDA-core fp64 rate bounds the scalar kernels (2 x 4096 x 64: Gram 21 us, solve 32 us); the same products on the fp64
+// tensor path.  Shared tiles are doubles with a 68-element pitch: both fragment patterns (row = lane & 3, column = base +
+// (lane >> 2), and row = base + (lane >> 2), column = lane & 3) then hit every bank pair exactly twice.
+constexpr int kCqLd = 68;
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// part[(b * gridDim.x + x)][i * r + j] (lower triangle) = X_b[rows]^T X_b[rows] over the 64-row blocks x, x + gridDim.x, ...
+__global__ void __launch_bounds__(256)
+cq_gram_mma_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, double* __restrict__ part, int m, int r,
+                   const int* __restrict__ only_if) {
+  pdl_trigger();
+  pdl_wait();
+  if (only_if != nullptr && only_if[blockIdx.y] == 0) return;
+  extern __shared__ __align__(16) double cq_mma_smem[];
+  double* sX = cq_mma_smem;                                  // [64 rows][kCqLd]
+  const float* Xb = X + blockIdx.y * x_bs;
+  double* G = part + (static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x) * (r * r);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int r8 = (r + 7) & ~7, rb = r8 >> 3;
+  const int fr = lane & 3, fc = lane >> 2;
+  double acc[8][2];
+#pragma unroll
+  for (int jb = 0; jb < 8; ++jb) acc[jb][0] = acc[jb][1] = 0.0;
+  for (int row0 = blockIdx.x * kCqGramRows; row0 < m; row0 += gridDim.x * kCqGramRows) {
+    __syncthreads();
+    for (int idx = tid; idx < kCqGramRows * r8; idx += 256) {
+      const int i = idx / r8, k = idx - i * r8;
+      sX[i * kCqLd + k] = (row0 + i < m && k < r) ? static_cast<double>(Xb[static_cast<int64_t>(row0 + i) * ldx + k]) : 0.0;
+    }
+    __syncthreads();
+    if (w < rb) {
+#pragma unroll 4
+      for (int ks = 0; ks < kCqGramRows / 4; ++ks) {
+        const double* rowp = sX + (4 * ks + fr) * kCqLd + fc;
+        const double a = rowp[8 * w];
+#pragma unroll
+        for (int jb = 0; jb < 8; ++jb)
+          if (jb <= w) dmma_8x8x4(acc[jb], a, rowp[8 * jb]);
+      }
+    }
+  }
+  if (w < rb) {
+#pragma unroll
+    for (int jb = 0; jb < 8; ++jb) {
+      if (jb > w) continue;
+      const int i = 8 * w + fc;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 8 * jb + 2 * fr + e;
+        if (i < r && j <= i) G[i * r + j] = acc[jb][e];
+      }
+    }
+  }
+}
+
+// Q = X . L^-T as a forward substitution blocked by 8 columns, 64 rows per CTA, a warp owns 8 rows:
+//   Y_j = X_j - sum_{b < j} Q_b . L[j-block, b-block]^T   (2 j MMAs on one accumulator),   Q_j = Y_j . inv(L_jj)^T   (2 MMAs)
+// Y_j and Q_j go back to the warp's rows of the shared X tile (the accumulator layout is not the A-operand layout), so only
+// __syncwarp separates the stages.
+__global__ void __launch_bounds__(256)
+cq_solve_mma_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __restrict__ Q, int64_t q_bs,
+                    const double* __restrict__ ws, int m, int r, const int* __restrict__ only_if) {
+  pdl_trigger();
+  pdl_wait();
+  if (only_if != nullptr && only_if[blockIdx.y] == 0) return;
+  extern __shared__ __align__(16) double cq_mma_smem[];
+  double* sX = cq_mma_smem;                                  // [64 rows][kCqLd]: x, then y, then q
+  double* sL = sX + 64 * kCqLd;                              // [64 j][kCqLd]: L[j][k]
+  double* sD = sL + 64 * kCqLd;                              // [64 k][kCqLd]: inv(L_bb)^T blocks (W of the Cholesky kernel)
+  const double* Gg = ws + blockIdx.y * kCqFac;
+  const double* Wg = Gg + kCqMaxR * kCqMaxR + kCqMaxR;
+  const float* Xb = X + blockIdx.y * x_bs;
+  float* Qb = Q + blockIdx.y * q_bs;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int r8 = (r + 7) & ~7, rb = r8 >> 3;
+  const int fr = lane & 3, fc = lane >> 2;
+  const int row0 = blockIdx.x * 64;
+  for (int idx = tid; idx < r8 * r8; idx += 256) {
+    const int j = idx / r8, k = idx - j * r8;
+    sL[j * kCqLd + k] = (j < r && k <= j) ? Gg[j * kCqMaxR + k] : 0.0;
+    sD[j * kCqLd + k] = Wg[j * kCqMaxR + k];
+  }
+  for (int idx = tid; idx < 64 * r8; idx += 256) {
+    const int i = idx / r8, k = idx - i * r8;
+    sX[i * kCqLd + k] = (row0 + i < m && k < r) ? static_cast<double>(Xb[static_cast<int64_t>(row0 + i) * ldx + k]) : 0.0;
+  }
+  __syncthreads();
+  double* xw = sX + (8 * w) * kCqLd;                          // this warp's 8 rows
+  const int row = row0 + 8 * w + fc;
+  for (int jb = 0; jb < rb; ++jb) {
+    double acc[2];
+    acc[0] = xw[fc * kCqLd + 8 * jb + 2 * fr];
+    acc[1] = xw[fc * kCqLd + 8 * jb + 2 * fr + 1];
+    // Y_j: minus the finished blocks; A = -Q[:, k0..k0+3], B[kk][jj] = L[8 jb + jj][k0 + kk]
+    for (int ks = 0; ks < 2 * jb; ++ks) {
+      const double a = -xw[fc * kCqLd + 4 * ks + fr];
+      const double bq = sL[(8 * jb + fc) * kCqLd + 4 * ks + fr];
+      dmma_8x8x4(acc, a, bq);
+    }
+    __syncwarp();
+    xw[fc * kCqLd + 8 * jb + 2 * fr] = acc[0];
+    xw[fc * kCqLd + 8 * jb + 2 * fr + 1] = acc[1];
+    __syncwarp();
+    // Q_j = Y_j . inv(L_jj)^T: B[kk][jj] = sD[8 jb + k0 + kk][8 jb + jj]
+    double q[2] = {0.0, 0.0};
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const double a = xw[fc * kCqLd + 8 * jb + 4 * s2 + fr];
+      const double bq = sD[(8 * jb + 4 * s2 + fr) * kCqLd + 8 * jb + fc];
+      dmma_8x8x4(q, a, bq);
+    }
+    __syncwarp();
+    xw[fc * kCqLd + 8 * jb + 2 * fr] = q[0];
+    xw[fc * kCqLd + 8 * jb + 2 * fr + 1] = q[1];
+    __syncwarp();
+    if (row < m) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 8 * jb + 2 * fr + e;
+        if (j < r) Qb[static_cast<int64_t>(row) * r + j] = static_cast<float>(q[e]);
+      }
+    }
+  }
 }
 
 // Q[row, :] = x_row . R^-1 with R = L^T:  q_j = (x_j - sum_{k<j} q_k L_jk) * dinv_j, one row per thread, fp64.
@@ -329,7 +492,7 @@ cq_solve_kernel(const float* __restrict__ X, int64_t x_bs, int ldx, float* __res
   double (*sL)[kCqMaxR + 1] = reinterpret_cast<double (*)[kCqMaxR + 1]>(cq_smem);   // sL[k][j] = L_jk (broadcast reads)
   double* sdinv = cq_smem + kCqMaxR * (kCqMaxR + 1);
   float (*sx)[kCqMaxR + 1] = reinterpret_cast<float (*)[kCqMaxR + 1]>(sdinv + kCqMaxR);
-  const double* G = ws + blockIdx.y * (kCqMaxR * kCqMaxR + kCqMaxR);
+  const double* G = ws + blockIdx.y * kCqFac;
   const float* Xb = X + blockIdx.y * x_bs;
   float* Qb = Q + blockIdx.y * q_bs;
   const int tid = threadIdx.x;
@@ -2202,8 +2365,13 @@ int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64
     double* part = reinterpret_cast<double*>(w8 + pl.part_off);
     dim3 ggrid(pl.n_part, batch);
     dim3 grid(ceil_div(m, kCqRows), batch);
+    static const bool mma_solve_enabled = [] { const char* e = getenv("SOWB_QR_MMA"); return e == nullptr || atoi(e) != 0; }();
+    const bool use_mma_solve = mma_solve_enabled && r > 16;
     constexpr size_t solve_smem = (kCqMaxR * (kCqMaxR + 1) + kCqMaxR) * sizeof(double) + size_t(kCqRows) * (kCqMaxR + 1) * sizeof(float);
     auto solve = [&](const float* src, int64_t bs, int ld, const double* fac, const int* only_if) -> cudaError_t {
+      if (use_mma_solve)
+        return launch_pdl(cq_solve_mma_kernel, dim3(ceil_div(m, 64), batch), dim3(256), size_t(3) * 64 * kCqLd * sizeof(double),
+                          stream, src, bs, ld, Q, q_batch_stride, fac, m, r, only_if);
 #define SOWB_CQ_SOLVE(RQ)                                                                                               \
   do {                                                                                                                  \
     cudaError_t e_ = set_max_smem_once(cq_solve_kernel<RQ>, solve_smem);                                                \
@@ -2217,7 +2385,19 @@ int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64
       SOWB_CQ_SOLVE(64);
 #undef SOWB_CQ_SOLVE
     };
+    // ranks above 16: Gram and solve on the fp64 tensor path (SOWB_QR_MMA=0 keeps the scalar kernels)
+    static const bool mma_enabled = [] { const char* e = getenv("SOWB_QR_MMA"); return e == nullptr || atoi(e) != 0; }();
+    const bool use_mma = mma_enabled && r > 16;
+    constexpr size_t chol_smem = (size_t(2) * kCqMaxR * (kCqMaxR + 1) + 2 * kCqMaxR) * sizeof(double);
+    constexpr size_t gram_mma_smem = size_t(kCqGramRows) * kCqLd * sizeof(double);
+    constexpr size_t solve_mma_smem = size_t(3) * 64 * kCqLd * sizeof(double);
+    SOWB_CHECK_CUDA(set_max_smem_once(cq_chol_kernel, chol_smem));
+    if (use_mma) {
+      SOWB_CHECK_CUDA(set_max_smem_once(cq_gram_mma_kernel, gram_mma_smem));
+      SOWB_CHECK_CUDA(set_max_smem_once(cq_solve_mma_kernel, solve_mma_smem));
+    }
     auto gram = [&](const float* src, int64_t bs, int ld, const int* only_if) -> cudaError_t {
+      if (use_mma) return launch_pdl(cq_gram_mma_kernel, ggrid, dim3(256), gram_mma_smem, stream, src, bs, ld, part, m, r, only_if);
       switch (ceil_div(r, 16)) {
         case 1: return launch_pdl(cq_gram_kernel<1>, ggrid, dim3(256), 0, stream, src, bs, ld, part, m, r, only_if);
         case 2: return launch_pdl(cq_gram_kernel<2>, ggrid, dim3(256), 0, stream, src, bs, ld, part, m, r, only_if);
@@ -2232,15 +2412,15 @@ int sow_thin_qr(const float* X, int64_t x_batch_stride, int ldx, float* Q, int64
     const bool fuse_sum = r <= 32;
     const double* no_part = nullptr;
     if (!fuse_sum) SOWB_CHECK_CUDA(launch_pdl(cq_sum_kernel, sgrid, dim3(256), 0, stream, part, pl.n_part, r, wsd, nullptr));
-    SOWB_CHECK_CUDA(launch_pdl(cq_chol_kernel, dim3(batch), dim3(1024), 0, stream, wsd, fuse_sum ? part : no_part, pl.n_part, r,
-                               flags, nullptr));
+    SOWB_CHECK_CUDA(launch_pdl(cq_chol_kernel, dim3(batch), dim3(1024), chol_smem, stream, wsd, fuse_sum ? part : no_part,
+                               pl.n_part, r, flags, nullptr, use_mma ? 1 : 0));
     SOWB_CHECK_CUDA(solve(X, x_batch_stride, ldx, wsd, nullptr));
     // CholeskyQR2 for the flagged matrices only: Q <- Q . chol(Q^T Q)^-T, in place
     SOWB_CHECK_CUDA(gram(Q, q_batch_stride, r, flags));
     SOWB_CHECK_CUDA(cudaGetLastError());
     if (!fuse_sum) SOWB_CHECK_CUDA(launch_pdl(cq_sum_kernel, sgrid, dim3(256), 0, stream, part, pl.n_part, r, wsd2, flags));
-    SOWB_CHECK_CUDA(launch_pdl(cq_chol_kernel, dim3(batch), dim3(1024), 0, stream, wsd2, fuse_sum ? part : no_part, pl.n_part, r,
-                               nullptr, flags));
+    SOWB_CHECK_CUDA(launch_pdl(cq_chol_kernel, dim3(batch), dim3(1024), chol_smem, stream, wsd2, fuse_sum ? part : no_part,
+                               pl.n_part, r, nullptr, flags, use_mma ? 1 : 0));
     SOWB_CHECK_CUDA(solve(Q, q_batch_stride, r, wsd2, flags));
     return SOWB_OK;
   }
