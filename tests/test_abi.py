@@ -70,3 +70,23 @@ def test_product_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     src = open(os.path.join(dirpath, f)).read()
                     assert "oracle" not in src.replace("sow_oracle_free", ""), os.path.join(dirpath, f)
+
+
+def test_workspace_queries_run_without_a_gpu():
+    """The *_workspace_bytes entry points are pure host arithmetic: callable here, positive for supported shapes, 0 where the
+    one-call TT entry points do not take the ranks (callers then keep the op-by-op path)."""
+    from sow_b200 import _lib
+    lib = _lib.load()
+    assert lib.sow_thin_qr_workspace_bytes(4096, 64, 2) > lib.sow_thin_qr_workspace_bytes(4096, 8, 2) > 0
+    assert lib.sow_thin_qr_workspace_bytes(4096, 100, 1) == 4096 * 100 * 4          # Gram-Schmidt path above rank 64
+    assert lib.tt_project_workspace_bytes(4096, 4096, 8, 1) > 0
+    assert lib.tt_project2_workspace_bytes(64, 64, 16) >= lib.tt_project_workspace_bytes(4096, 4096, 16, 1)
+    assert lib.tt_adam2_workspace_bytes(64, 64) > lib.tt_adam2_fused_workspace_bytes(64, 64) > 0
+    ok = (ctypes.c_int * 4)(1, 8, 8, 1)
+    bad_rank = (ctypes.c_int * 4)(1, 128, 8, 1)
+    bad_edge = (ctypes.c_int * 4)(2, 8, 8, 1)
+    assert lib.tt_nd_workspace_bytes(16, 16, 3, ok) > 0
+    assert lib.tt_adam_nd_workspace_bytes(16, 16, 3, ok) > lib.tt_nd_workspace_bytes(16, 16, 3, ok)
+    assert lib.tt_nd_workspace_bytes(16, 16, 3, bad_rank) == 0
+    assert lib.tt_adam_nd_workspace_bytes(16, 16, 3, bad_edge) == 0
+    assert lib.tt_adam_nd_workspace_bytes(16, 16, 2, (ctypes.c_int * 3)(1, 8, 1)) == 0   # order 2 has its own entry point
