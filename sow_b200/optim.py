@@ -37,6 +37,11 @@ class TTAdam(torch.optim.Optimizer):
         loss = None
         if closure is not None:
             loss = closure()
+        # Tensor-train parameters are independent of each other and each one's step is a chain of small dependent kernels (head,
+        # Cholesky-QR) in front of one large kernel: consecutive parameters alternate between side streams, so the chain of
+        # one overlaps the large kernel of another.  The side streams fork from / join the caller's stream around the step.
+        n_side = self._side_stream_count()
+        side, used, forked, tt_index = None, set(), None, 0
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             for p in group["params"]:
@@ -61,11 +66,45 @@ class TTAdam(torch.optim.Optimizer):
                 if "ranks" in group and grad.dim() == 2:
                     if not hasattr(self, "_tt2_plans"):
                         self._tt2_plans = {}           # per-parameter plans of the fused order-2 path (not part of state_dict)
-                    self._tt_update(p, grad, state, list(group["ranks"]), first, beta1, beta2, group["eps"], step_size, lr_wd,
-                                    self._tt2_plans)
+                    if n_side > 1:
+                        if side is None:
+                            side = self._side_streams(p.device, n_side)
+                            forked = torch.cuda.current_stream(p.device).record_event()
+                        k = tt_index % n_side
+                        tt_index += 1
+                        if k not in used:
+                            side[k].wait_event(forked)
+                            used.add(k)
+                        with torch.cuda.stream(side[k]):
+                            self._tt_update(p, grad, state, list(group["ranks"]), first, beta1, beta2, group["eps"], step_size,
+                                            lr_wd, self._tt2_plans)
+                    else:
+                        self._tt_update(p, grad, state, list(group["ranks"]), first, beta1, beta2, group["eps"], step_size, lr_wd,
+                                        self._tt2_plans)
                 else:
                     self._dense_update(p, grad, state, first, beta1, beta2, group["eps"], step_size, lr_wd)
+        if side is not None:
+            cur = torch.cuda.current_stream(side[0].device)
+            for k in used:
+                cur.wait_event(side[k].record_event())
         return loss
+
+    def _side_stream_count(self) -> int:
+        """Streams the tensor-train parameters alternate on (SOWB_TT_STREAMS, default 4; 1 = everything on the caller's
+        stream).  Only worth it with more than one tensor-train parameter."""
+        import os
+        n = int(os.environ.get("SOWB_TT_STREAMS", "4"))
+        if n <= 1:
+            return 1
+        n_tt = sum(1 for g in self.param_groups if "ranks" in g for p in g["params"] if p.grad is not None and p.grad.dim() == 2)
+        return n if n_tt > 1 else 1
+
+    def _side_streams(self, device, n):
+        cache = self.__dict__.setdefault("_tt_streams", {})
+        key = (device.index, n)
+        if key not in cache:
+            cache[key] = [torch.cuda.Stream(device=device, priority=-1) for _ in range(n)]
+        return cache[key]
 
     @staticmethod
     def _dense_update(p, grad, state, first, beta1, beta2, eps, step_size, lr_wd):

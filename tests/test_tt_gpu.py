@@ -250,3 +250,28 @@ def test_ttadam_plan_survives_replaced_and_reset_state(golden_tt, case):
         p.copy_(torch.from_numpy(g[f"ttadam/{case}/p0"]).cuda())
     opt.step()
     assert torch.equal(p.detach(), p1)
+
+
+def test_ttadam_side_streams_do_not_change_the_result(monkeypatch):
+    """Several tensor-train parameters alternate between side streams inside TTAdam.step (the small QR chain of one overlaps the
+    large kernel of another); the parameters are independent, so the result is bit-identical to the one-stream order."""
+    from tn_gradient.optimizer.ttadam import TTAdam
+
+    def run(streams):
+        monkeypatch.setenv("SOWB_TT_STREAMS", str(streams))
+        torch.manual_seed(11)
+        ps = [torch.nn.Parameter(torch.randn(256, 320, device="cuda")) for _ in range(5)]
+        ps.append(torch.nn.Parameter(torch.randn(64, device="cuda")))            # a dense one in the same optimizer
+        opt = TTAdam([{"params": ps[:5], "ranks": [1, 8, 1]}, {"params": ps[5:]}], lr=1e-2)
+        for step in range(4):
+            gen = torch.Generator(device="cuda").manual_seed(100 + step)
+            for p in ps:
+                p.grad = torch.randn(p.shape, device="cuda", generator=gen)
+            opt.step()
+        torch.cuda.synchronize()
+        return [p.detach().clone() for p in ps]
+
+    ref = run(1)
+    for streams in (2, 4):
+        for a, b in zip(ref, run(streams)):
+            assert torch.equal(a, b)
