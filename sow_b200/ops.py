@@ -49,16 +49,21 @@ def _dtype_code(dt: torch.dtype) -> int:
     raise SowB200Error(f"unsupported dtype {dt}")
 
 
-def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+def workspace(device: torch.device, nbytes: int, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
     """Per-(device, stream) scratch buffer, grown on demand.  Kernels that share a stream are serialised, so one
     buffer per stream is enough; a bigger request replaces the buffer (the old one stays alive until the work
-    queued on it finishes because the caching allocator is stream-ordered)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
+    queued on it finishes because the caching allocator is stream-ordered).  ``stream``: the stream the caller will
+    launch on when that is not the current one (the buffer is then allocated under it)."""
+    sp = stream.cuda_stream if stream is not None else torch.cuda.current_stream(device).cuda_stream
+    key = (device.index if device.index is not None else torch.cuda.current_device(), sp)
     with _ws_lock:
         buf = _workspaces.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            if stream is not None:
+                with torch.cuda.stream(stream):
+                    buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            else:
+                buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
             _workspaces[key] = buf
     return buf
 
@@ -446,18 +451,20 @@ class TTAdam2Plan:
         mm, nn, r = self.mm, self.nn, self.r
         return tuple((self.Q[k][b].reshape(1, mm, nn, r), self.R[k][b].reshape(r, mm, nn, 1)) for b in range(2))
 
-    def step(self, p, g, beta1, beta2, eps, step_size, lr_wd) -> int:
-        """One update of p from g; returns the index of the core set that now holds the moments."""
+    def step(self, p, g, beta1, beta2, eps, step_size, lr_wd, stream=None) -> int:
+        """One update of p from g (on ``stream`` when given, else on the current stream); returns the index of the core
+        set that now holds the moments."""
         lib = _lib.load()
         first = self.cur < 0
         out = 0 if first else 1 - self.cur
         g1m, g2m, g1v, g2v = (None, None, None, None) if first else self._ptr[self.cur]
         qm, rm, qv, rv = self._ptr[out]
         M, N = p.shape
-        ws = workspace(self.device, self.ws_bytes)
+        ws = workspace(self.device, self.ws_bytes, stream)
+        sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream_ptr(self.device)
         rc = lib.tt_adam2_step(_p(p), _p(g), g1m, g2m, g1v, g2v, self.r, qm, qv, rm, rv, M, N, self.mm, self.nn,
                                float(beta1), float(beta2), float(eps), float(step_size), float(lr_wd), 1 if first else 0,
-                               _dtype_code(p.dtype), _p(ws), ws.numel(), _stream_ptr(self.device))
+                               _dtype_code(p.dtype), _p(ws), ws.numel(), sp)
         check(rc, "tt_adam2_step")
         launch_counter["kernels"] += 8
         self.cur = out
@@ -536,16 +543,16 @@ class TTAdamNPlan:
         rk = self.ranks
         return [self.bufs[s][k][b].reshape(rk[k], self.mm, self.nn, rk[k + 1]) for k in range(self.order)]
 
-    def step(self, p, g, beta1, beta2, eps, step_size, lr_wd) -> int:
+    def step(self, p, g, beta1, beta2, eps, step_size, lr_wd, stream=None) -> int:
         lib = _lib.load()
         first = self.cur < 0
         out = 0 if first else 1 - self.cur
         M, N = p.shape
-        ws = workspace(self.device, self.ws_bytes)
+        ws = workspace(self.device, self.ws_bytes, stream)
+        sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream_ptr(self.device)
         rc = lib.tt_adam_nd_step(_p(p), _p(g), None if first else self._tab[self.cur], self._tab[out], self._ranks_c, M, N,
                                self.mm, self.nn, self.order, float(beta1), float(beta2), float(eps), float(step_size),
-                               float(lr_wd), 1 if first else 0, _dtype_code(p.dtype), _p(ws), ws.numel(),
-                               _stream_ptr(self.device))
+                               float(lr_wd), 1 if first else 0, _dtype_code(p.dtype), _p(ws), ws.numel(), sp)
         check(rc, "tt_adam_nd_step")
         launch_counter["kernels"] += 2 * (self.order - 1) + 1 + 8 * (self.order - 1)
         self.cur = out

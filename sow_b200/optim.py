@@ -66,6 +66,7 @@ class TTAdam(torch.optim.Optimizer):
                 if "ranks" in group and grad.dim() == 2:
                     if not hasattr(self, "_tt2_plans"):
                         self._tt2_plans = {}           # per-parameter plans of the fused order-2 path (not part of state_dict)
+                    stream = None
                     if n_side > 1:
                         if side is None:
                             side = self._side_streams(p.device, n_side)
@@ -75,7 +76,14 @@ class TTAdam(torch.optim.Optimizer):
                         if k not in used:
                             side[k].wait_event(forked)
                             used.add(k)
-                        with torch.cuda.stream(side[k]):
+                        stream = side[k]
+                    # steady state: a live plan takes the step as one C-ABI call on the given stream (no stream switch, no
+                    # shape arithmetic); everything else (first step, re-seeding, ranks without a plan) goes the long way
+                    if self._plan_step(p, grad, state, group["ranks"], first, beta1, beta2, group["eps"], step_size, lr_wd,
+                                       stream):
+                        continue
+                    if stream is not None:
+                        with torch.cuda.stream(stream):
                             self._tt_update(p, grad, state, list(group["ranks"]), first, beta1, beta2, group["eps"], step_size,
                                             lr_wd, self._tt2_plans)
                     else:
@@ -88,6 +96,28 @@ class TTAdam(torch.optim.Optimizer):
             for k in used:
                 cur.wait_event(side[k].record_event())
         return loss
+
+    def _plan_step(self, p, grad, state, ranks, first, beta1, beta2, eps, step_size, lr_wd, stream) -> bool:
+        """The step through an existing, live per-parameter plan (see _tt_update for how plans are made and re-seeded)."""
+        if first or grad.dtype != p.dtype or not grad.is_contiguous():
+            return False
+        order = len(ranks) - 1
+        plan = self._tt2_plans.get(p) if order == 2 else self._tt2_plans.get("_order_n", {}).get(p)
+        if plan is None or plan.cur < 0 or not getattr(plan, "supported", True):
+            return False
+        if (plan.r != ranks[1]) if order == 2 else (plan.ranks != [int(r) for r in ranks]):
+            return False
+        tts = plan.tts[plan.cur]
+        if state.get("exp_avg") is not tts[0] or state.get("exp_avg_sq") is not tts[1]:
+            return False
+        pd = p.data
+        if not pd.is_contiguous():
+            return False
+        state["exp_avg_expr"] = tts[0].contract_expr                      # ttadam.py:73,81
+        state["exp_avg_sq_expr"] = tts[1].contract_expr
+        k = plan.step(pd, grad, beta1, beta2, eps, step_size, lr_wd, stream=stream)
+        state["exp_avg"], state["exp_avg_sq"] = plan.tts[k]
+        return True
 
     def _side_stream_count(self) -> int:
         """Streams the tensor-train parameters alternate on (SOWB_TT_STREAMS, default 4; 1 = everything on the caller's
