@@ -3,7 +3,8 @@
     python tools/sass_histogram.py > profiles/r02_sass_histogram.txt
 UTCHMMA = tcgen05.mma (kind::f16), UTMALDG / UTMASTG = TMA tensor load / store, UTMAPF = TMA L2 prefetch, UBLKCP / UBLKPF = bulk
 copy / prefetch, LDTM / STTM = tcgen05.ld / st (TMEM), UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM alloc, SYNCS = mbarrier,
-UCGABAR = cluster barrier, MAPA / ST.E...CLUSTER via 'MAPA'.
+UCGABAR = cluster barrier, MAPA / ST.E...CLUSTER via 'MAPA', DMMA = fp64 mma.sync (Cholesky-QR above rank 16), LDGSTS = cp.async,
+ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents (programmatic dependent launch).
 """
 import collections
 import os
@@ -14,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "sow_b200", "csrc", "libsow_b200.so")
 OPS = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "UBLKPF", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS",
-       "SYNCS", "UCGABAR", "MAPA", "UMAPA", "HMMA", "FFMA", "DFMA"]
+       "SYNCS", "UCGABAR", "MAPA", "UMAPA", "HMMA", "DMMA", "FFMA", "DFMA", "LDGSTS", "ACQBULK", "PREEXIT"]
 
 
 def main():
